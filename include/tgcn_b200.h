@@ -1,0 +1,178 @@
+/*
+ * tgcn_b200.h — C ABI of libtgcn_b200.so: the sm_100a kernels beneath TextGCN's LightGCN hot path.
+ *
+ * The reference (sergey-volokhin/TextGCN) has no FFI: its plugin surface is Python method
+ * override on BaseModel.  Each entry point below replaces the ATen call chain of
+ * one of those methods; the cited file:line is the reference code it stands in for (paths under
+ * the reference's TextGCN/ package).  INTEGRATION.md shows the ctypes binding and the subclass a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - Every pointer named d_* is a DEVICE pointer, h_* a HOST pointer.  No torch types appear here.
+ *   - All matrices are row-major fp32; index arrays are int32; all calls are asynchronous on
+ *     `stream` (a cudaStream_t passed as void*), never synchronise, and allocate nothing:
+ *     the caller owns inputs, outputs and workspaces.  Only graph handles own device memory.
+ *   - Node numbering follows the reference: rows [0, n_users) are users, rows [n_users, n_users +
+ *     n_items) are items (dataset.py:130-131).  N = n_users + n_items.
+ *   - Return value 0 = ok; otherwise tgcn_last_error() (thread-local) describes the failure.
+ *     There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - Embedding width d must be a multiple of 4 and rows 16-byte aligned (128-bit loads).
+ */
+#ifndef TGCN_B200_H
+#define TGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGCN_ABI_VERSION 1
+#define TGCN_MAX_LAYERS 15
+#define TGCN_MAX_TOPK 128
+#define TGCN_ADV_MAX_CANDIDATES 2048
+
+typedef struct tgcn_graph tgcn_graph_t;
+typedef void* tgcn_stream_t; /* cudaStream_t */
+
+int tgcn_abi_version(void);
+const char* tgcn_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph handle.  Consumes Â exactly as dataset.norm_matrix holds it (dataset.py:122-157): the
+ * coalesced COO sorted by (row, col) IS CSR order, so the caller passes rowptr (N+1), col (nnz)
+ * and val (nnz) on the device.  The arrays are borrowed and must outlive the handle.  The handle
+ * owns: the long-row segment list used for load balancing and (built on first need) the
+ * transpose permutation tperm[p] = position of entry (c, r) for entry p = (r, c), which lets the
+ * backward pass apply Â_dropᵀ without rebuilding a matrix (base_model.py:77-86).
+ * --------------------------------------------------------------------------------------------- */
+int tgcn_graph_create(tgcn_graph_t** out, int64_t n_users, int64_t n_items, int64_t nnz,
+                      const int32_t* d_rowptr, const int32_t* d_col, const float* d_val,
+                      tgcn_stream_t stream);
+/* Row-block variant for multi-GPU: the handle covers rows [row_begin, row_begin + n_local_rows) of Â;
+ * d_rowptr has n_local_rows + 1 entries starting at 0; d_col holds indices into the gathered table. */
+int tgcn_graph_create_block(tgcn_graph_t** out, int64_t n_users, int64_t n_items, int64_t row_begin,
+                            int64_t n_local_rows, int64_t nnz_local, const int32_t* d_rowptr,
+                            const int32_t* d_col, const float* d_val, tgcn_stream_t stream);
+int tgcn_graph_build_transpose_perm(tgcn_graph_t* g, tgcn_stream_t stream);
+void tgcn_graph_destroy(tgcn_graph_t* g);
+int64_t tgcn_graph_num_segments(const tgcn_graph_t* g);
+/* bytes of caller-provided workspace for propagate_fwd / propagate_bwd */
+int64_t tgcn_propagate_workspace_bytes(const tgcn_graph_t* g, int64_t d, int32_t n_layers);
+
+/* a4  BaseModel.layer_aggregation (base_model.py:141-148): Y = Â · X, X and Y are (N, d). */
+int tgcn_spmm_fwd(const tgcn_graph_t* g, int64_t d, const float* d_x, float* d_y,
+                  void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* a4 with a3/a5 fused: one SpMM pass  Y = (add_0 + ... + add_{n_add-1} + Â·X) / divisor  [+ Y if accumulate].
+ * X is read through two base pointers (d_x_item NULL = contiguous after the user rows); d_keep/dropout apply the
+ * edge-dropout mask (transposed != 0 applies Â_dropᵀ through the transpose permutation).  h_add_user / h_add_item
+ * are HOST arrays of n_add device pointers (item part NULL = contiguous).  This is the per-hop building block the
+ * multi-GPU host code calls between all-gathers; for a row-block handle X is the gathered table indexed by d_col
+ * and Y / addends are the local rows. */
+int tgcn_spmm_ex(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const float* d_x_item,
+                 const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
+                 const float* const* h_add_user, const float* const* h_add_item, float divisor,
+                 int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* a2+a3+a4×L+a5  BaseModel.representation (base_model.py:88-106, :150-164).
+ * E0 is read through two base pointers (no torch.cat); d_keep is the Bernoulli keep-mask over the
+ * nnz of Â drawn by the caller (base_model.py:82) or NULL in eval mode; survivors are scaled by
+ * 1/(1-dropout) (:84).  single != 0 returns the last layer (:159-164) instead of the mean (:157).
+ * d_out is (N, d): rows [0,n_users) users_emb, the rest items_emb (:106). */
+int tgcn_propagate_fwd(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single,
+                       const float* d_user_w, const float* d_item_w, const uint8_t* d_keep, float dropout,
+                       float* d_out, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* Backward of the above (what autograd does at base_model.py:125 through :148/:157): given
+ * d_grad_out = dL/d(out) (N, d) computes dL/dE0 into d_grad_in (N, d) with L transposed SpMMs in
+ * Horner form and no saved activations.  accumulate != 0 adds into d_grad_in instead of storing. */
+int tgcn_propagate_bwd(tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single,
+                       const float* d_grad_out, const uint8_t* d_keep, float dropout, int32_t accumulate,
+                       float* d_grad_in, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* Host-buffer form of representation for callers that keep the tables in host memory: copies
+ * h_user_w / h_item_w to the device staging buffers the caller provides, runs propagate_fwd and
+ * copies the (N, d) result back to h_out, all on `stream`.  d_stage must hold 2·N·d floats. */
+int tgcn_propagate_host(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single,
+                        const float* h_user_w, const float* h_item_w, float* h_out,
+                        float* d_stage, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* a7-a10  bpr_loss + reg_loss (base_model.py:166-171, :186-210) and their gradients, one kernel.
+ * d_emb is the (N, d) result of propagate_fwd; d_user_w/d_item_w the layer-0 tables.  d_negs is
+ * (n_neg, batch).  Loss is mean over negatives of mean(SELU(neg - pos)) (:194); the regulariser is
+ * reg_lambda/(2·batch)·(‖U0[users]‖² + ‖I0[pos]‖² + ‖I0[negs]‖²_F) (:200-210).
+ * Outputs: d_losses[0] = bpr, d_losses[1] = reg; dL/d(emb) is atomically ADDED into d_grad_emb (N, d)
+ * and the regulariser's gradient into d_grad_w0 (N, d) (either may be NULL to skip; caller zeroes).
+ * d_workspace holds per-warp partial sums: tgcn_bpr_workspace_bytes(batch). */
+int64_t tgcn_bpr_workspace_bytes(int64_t batch);
+int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch, int32_t n_neg,
+                     const int32_t* d_users, const int32_t* d_pos, const int32_t* d_negs,
+                     const float* d_emb, const float* d_user_w, const float* d_item_w, float reg_lambda,
+                     float* d_losses, float* d_grad_emb, float* d_grad_w0,
+                     void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* a11+a12  score_batchwise + train-item masking + topk (base_model.py:173-179, :255-261) fused:
+ * the (n_rank, n_items) score matrix never reaches HBM.  Ranks users d_users[0..n_rank) (NULL = ids
+ * 0..n_rank-1) against items [item_begin, item_end).  Vectors: d_user_vecs row u at u·ldu, item row i
+ * at i·ldi, K floats each (K % 4 == 0).  score = <user, item> (+ d_user_bias[u]) (+ d_item_bias[i]).
+ * vecs_by_position != 0: user vectors and d_user_bias are indexed by list position m instead of user id
+ * d_users[m] (packed LTR operands); d_users is then used for the mask only.
+ * Items the user interacted with in `mask_graph` (user rows of Â = train_user_dict) are excluded;
+ * when fewer than k unmasked items exist the list is completed with masked items, lowest id first,
+ * score -inf.  Order is the canonical strict order (score desc, item id asc).
+ * Outputs (n_rank, k) int32 ids and fp32 scores.  k <= TGCN_MAX_TOPK. */
+int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int32_t k);
+int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users,
+                   const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K,
+                   int64_t item_begin, int64_t item_end, const float* d_user_bias, const float* d_item_bias,
+                   int32_t vecs_by_position, int32_t k, int32_t finalize, int32_t* d_out_ids, float* d_out_scores,
+                   void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* Cross-shard / cross-GPU merge of n_parts partial top-k tables (n_parts, n_rows, k) under the same
+ * order; finalize != 0 applies the G9 completion using mask_graph and d_users. */
+int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_t* d_users, int32_t n_parts,
+                    int32_t k, const int32_t* d_part_ids, const float* d_part_scores, int32_t finalize,
+                    int32_t* d_out_ids, float* d_out_scores, tgcn_stream_t stream);
+
+/* a15+a16  AdvSamplModel.score_pairwise_adv + per-user sort / positive removal / top max(k)
+ * (advanced_sampling.py:37-44, :61-65; utils.py:121-128) as one kernel: for each batch row scores its
+ * n_cand candidates, orders them (score desc, candidate position asc), drops the user's train items and
+ * writes the first kmax to d_out_negs (batch, kmax), -1 padded, with counts in d_out_counts. */
+int tgcn_adv_select(const tgcn_graph_t* mask_graph, int64_t d, int64_t batch, int32_t n_cand,
+                    const int32_t* d_users, const int32_t* d_cands, const float* d_emb, int32_t kmax,
+                    int32_t* d_out_negs, int32_t* d_out_counts, float* d_out_scores, tgcn_stream_t stream);
+
+/* a17-a21  LTR feature assembly (ltr_models.py:116-166, :200-241).
+ * pairwise_features: for pair b = (users[b], items[b]) writes the 5 raw dot products
+ *   [emb·emb, rev·rev, desc·desc, rev·desc, desc·rev] (:154-163) to d_out (batch, n_feat) columns 0..4,
+ *   and, if n_feat == 7, popularity_users[u], popularity_items[i] to columns 5, 6 (:234-241).
+ * pairwise_emb_bwd: scatter-adds d(feature 0)/d(emb) given d_gf0 (batch) into d_grad_emb (N, d).
+ * pack_items / pack_users: operands of the collapsed batchwise score (the head has no activation,
+ *   ltr_models.py:186-190): item row = [w0·Ie | w1·Ir + w3·Id | w2·Id + w4·Ir], user row = [Ue | Ur | Ud],
+ *   so score_batchwise_ltr (:200-204) is one contraction of width d + 2·D fed to tgcn_eval_topk. */
+int tgcn_ltr_pairwise_features(int64_t n_users, int64_t d, int64_t D, int64_t batch, int32_t n_feat,
+                               const int32_t* d_users, const int32_t* d_items, const float* d_emb,
+                               const float* d_users_rev, const float* d_users_desc,
+                               const float* d_items_rev, const float* d_items_desc,
+                               const float* d_pop_users, const float* d_pop_items,
+                               float* d_out, tgcn_stream_t stream);
+int tgcn_ltr_pairwise_emb_bwd(int64_t n_users, int64_t d, int64_t batch, const int32_t* d_users,
+                              const int32_t* d_items, const float* d_emb, const float* d_gf0,
+                              float* d_grad_emb, tgcn_stream_t stream);
+int tgcn_ltr_pack_items(int64_t n_items, int64_t d, int64_t D, const float* d_items_emb,
+                        const float* d_items_rev, const float* d_items_desc, const float* h_w5,
+                        float* d_out, tgcn_stream_t stream);
+int tgcn_ltr_pack_users(int64_t n_rank, const int32_t* d_users, int64_t d, int64_t D,
+                        const float* d_users_emb, const float* d_users_rev, const float* d_users_desc,
+                        float* d_out, tgcn_stream_t stream);
+
+/* n3 (next row)  dense Adam step over one table, torch.optim.Adam defaults (base_model.py:111, :126):
+ * p, m, v updated in place from g; step is the 1-based step count. */
+int tgcn_adam_step(int64_t n, float* d_p, const float* d_g, float* d_m, float* d_v, float lr, float beta1,
+                   float beta2, float eps, int64_t step, tgcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGCN_B200_H */

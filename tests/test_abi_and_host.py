@@ -1,0 +1,91 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; host-side logic that needs no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import lightgcn_oracle as O
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tgcn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tgcn_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as entry
+    entry.build()
+    from textgcn_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from textgcn_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tgcn_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(declared)
+    assert lib.tgcn_abi_version() == _lib.ABI_VERSION
+
+
+def test_size_queries_and_argument_validation_without_gpu(lib):
+    assert lib.tgcn_bpr_workspace_bytes(2048) >= 2048 * 8
+    assert lib.tgcn_eval_workspace_bytes(2048, 63000, 20) > 0
+    assert lib.tgcn_eval_workspace_bytes(0, 63000, 20) < 0
+    # argument errors are reported through the return code + tgcn_last_error, never by aborting
+    rc = lib.tgcn_topk_merge(None, 0, None, 1, 20, None, None, 1, None, None, None)
+    assert rc != 0 and b"bad sizes" in lib.tgcn_last_error()
+    rc = lib.tgcn_eval_topk(None, 8, None, None, 64, None, 64, 63, 0, 10, None, None, 0, 20, 1, None, None, None, 0, None)
+    assert rc != 0 and b"bad shapes" in lib.tgcn_last_error()
+    handle = ctypes.c_void_p()
+    rc = lib.tgcn_graph_create(ctypes.byref(handle), 5, 4, 26, None, None, None, None)
+    assert rc != 0 and handle.value is None
+
+
+def test_product_refuses_cpu_tensors_and_never_imports_the_oracle():
+    from textgcn_b200 import TgcnError, ops
+    with pytest.raises(TgcnError):
+        ops.propagate_fwd(None, torch.zeros(4, 4), torch.zeros(4, 4), 1)
+    from textgcn_b200.models import BaseModel, make_params
+    with pytest.raises(TgcnError):
+        BaseModel(make_params(device=torch.device("cpu")), object())
+    pkg = os.path.join(ROOT, "textgcn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("parity oracle", ""), f"{f} references the oracle"
+
+
+@pytest.mark.parametrize("case", ["dummy_lgcn", "small_lgcn_d64", "small_adv"])
+def test_host_norm_adj_builder_is_bit_exact(case):
+    from textgcn_b200.graph import csr_to_norm_matrix, norm_adj_csr
+    g = load_golden(case)
+    rowptr, col, val = norm_adj_csr(torch.from_numpy(g["train_u"]), torch.from_numpy(g["train_i"]), int(g["n_users"]), int(g["n_items"]))
+    assert np.array_equal(col.numpy(), g["norm_col"])
+    assert np.array_equal(val.numpy().view(np.uint32), g["norm_val"].view(np.uint32))
+    nm = csr_to_norm_matrix(rowptr, col, val)
+    assert np.array_equal(nm.indices()[0].numpy(), g["norm_row"])
+
+
+def test_host_metrics_match_reference_golden():
+    from textgcn_b200 import metrics as M
+    for case in ["dummy_lgcn", "small_lgcn_d64", "small_lgcn_d128_l4"]:
+        g = load_golden(case)
+        test = O.train_lists_from_edges(g["test_u"], g["test_i"], int(g["n_users"]))
+        res = M.calculate_metrics(torch.from_numpy(g["pred_ids"]), [test[u].tolist() for u in g["test_users"]], g["ks"].tolist())
+        for m in M.METRICS:
+            assert np.allclose(res[m], g["metric_" + m], rtol=0, atol=1e-12), (case, m)
+    # duplicates in y_true count in the recall denominator, repeated predictions count once (np.intersect1d)
+    res = M.calculate_metrics(torch.tensor([[1, 1, 2]]), [[1, 1, 5]], [3])
+    ref = O.calculate_metrics([[1, 1, 2]], [[1, 1, 5]], [3])
+    for m in M.METRICS:
+        assert np.allclose(res[m], ref[m]), m

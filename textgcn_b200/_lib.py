@@ -1,0 +1,82 @@
+"""ctypes binding of libtgcn_b200.so (the C ABI declared in include/tgcn_b200.h).
+
+There is no CPU fallback: if the library has not been built, importing a compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libtgcn_b200.so")
+
+ABI_VERSION = 1
+MAX_TOPK = 128
+ADV_MAX_CANDIDATES = 2048
+
+_P = c_void_p  # device / host pointers travel as integers
+
+# name -> (restype, argtypes); every symbol include/tgcn_b200.h declares
+SIGNATURES = {
+    "tgcn_abi_version": (c_int32, []),
+    "tgcn_last_error": (c_char_p, []),
+    "tgcn_graph_create": (c_int32, [POINTER(c_void_p), c_int64, c_int64, c_int64, _P, _P, _P, _P]),
+    "tgcn_graph_create_block": (c_int32, [POINTER(c_void_p), c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
+    "tgcn_graph_build_transpose_perm": (c_int32, [_P, _P]),
+    "tgcn_graph_destroy": (None, [_P]),
+    "tgcn_graph_num_segments": (c_int64, [_P]),
+    "tgcn_propagate_workspace_bytes": (c_int64, [_P, c_int64, c_int32]),
+    "tgcn_spmm_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, _P]),
+    "tgcn_spmm_ex": (c_int32, [_P, c_int64, _P, _P, _P, c_float, c_int32, c_int32, POINTER(c_void_p), POINTER(c_void_p),
+                               c_float, c_int32, _P, _P, c_int64, _P]),
+    "tgcn_propagate_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, c_int64, _P]),
+    "tgcn_propagate_bwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, c_float, c_int32, _P, _P, c_int64, _P]),
+    "tgcn_propagate_host": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, c_int64, _P]),
+    "tgcn_bpr_workspace_bytes": (c_int64, [c_int64]),
+    "tgcn_bpr_fwd_bwd": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float,
+                                   _P, _P, _P, _P, c_int64, _P]),
+    "tgcn_eval_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
+    "tgcn_eval_topk": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
+                                 c_int32, c_int32, c_int32, _P, _P, _P, c_int64, _P]),
+    "tgcn_topk_merge": (c_int32, [_P, c_int64, _P, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P]),
+    "tgcn_adv_select": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P, _P]),
+    "tgcn_ltr_pairwise_features": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P,
+                                             _P, _P, _P, _P]),
+    "tgcn_ltr_pairwise_emb_bwd": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "tgcn_ltr_pack_items": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, POINTER(c_float), _P, _P]),
+    "tgcn_ltr_pack_users": (c_int32, [c_int64, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "tgcn_adam_step": (c_int32, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_int64, _P]),
+}
+
+_lib = None
+
+
+class TgcnError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and attach the signatures.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TgcnError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(textgcn_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.tgcn_abi_version()
+    if got != ABI_VERSION:
+        raise TgcnError(f"libtgcn_b200 ABI version {got} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TgcnError(load().tgcn_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,106 @@
+// Shared helpers for libtgcn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "tgcn_b200.h"
+
+namespace tgcn {
+
+void set_error(const char* fmt, ...);
+
+#define TGCN_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::tgcn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+#define TGCN_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::tgcn::set_error(__VA_ARGS__);    \
+      return 2;                          \
+    }                                    \
+  } while (0)
+
+#define TGCN_CHECK_LAUNCH() TGCN_CHECK_CUDA(cudaGetLastError())
+
+constexpr int kSplitThreshold = 512;  // rows longer than this are cut into segments
+constexpr int kSegmentLen = 256;      // nnz per segment of a long row
+
+struct Segment {  // one warp's share of a long row
+  int row;        // local row index
+  int begin;      // nnz range
+  int end;
+  int slot;       // index into the partial-sum scratch
+};
+struct SplitRow {
+  int row;
+  int first_slot;
+  int n_parts;
+  int pad;
+};
+
+}  // namespace tgcn
+
+struct tgcn_graph {
+  int64_t n_users, n_items;
+  int64_t row_begin;  // first global row covered (0 unless a row block)
+  int64_t n_rows;     // rows covered by this handle
+  int64_t nnz;
+  int is_block;
+  const int* rowptr;
+  const int* col;
+  const float* val;
+  int* tperm;  // owned, built on demand
+  tgcn::Segment* segments;
+  int n_segments;
+  tgcn::SplitRow* split_rows;
+  int n_split_rows;
+  int max_degree;
+};
+
+namespace tgcn {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x);
+  a.y = fmaf(s, x.y, a.y);
+  a.z = fmaf(s, x.z, a.z);
+  a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ void add4(float4& a, const float4& x) {
+  a.x += x.x;
+  a.y += x.y;
+  a.z += x.z;
+  a.w += x.w;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// strict total order used for every ranking: score descending, then id ascending
+__device__ __forceinline__ bool ranks_before(float sa, int ia, float sb, int ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+// true if `key` occurs in the sorted range col[lo, hi)
+__device__ __forceinline__ bool sorted_contains(const int* __restrict__ col, int lo, int hi, int key) {
+  const int end = hi;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    int c = __ldg(col + mid);
+    if (c < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo < end && __ldg(col + lo) == key;
+}
+
+}  // namespace tgcn

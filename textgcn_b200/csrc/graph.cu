@@ -1,0 +1,178 @@
+// Graph handle: borrowed CSR of Â + owned load-balancing metadata and transpose permutation.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace tgcn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// tperm[p] = q such that entry q is (c, r) when entry p is (r, c).  One thread per nnz.
+__global__ void transpose_perm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_rows,
+                                      int64_t nnz, int* __restrict__ tperm, int* __restrict__ missing) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  // row of p: largest r with rowptr[r] <= p
+  int lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(rowptr + mid) <= p) lo = mid;
+    else hi = mid;
+  }
+  const int r = lo;
+  const int c = __ldg(col + p);
+  int a = __ldg(rowptr + c), b = __ldg(rowptr + c + 1);
+  const int end = b;
+  while (a < b) {
+    int mid = (a + b) >> 1;
+    if (__ldg(col + mid) < r) a = mid + 1;
+    else b = mid;
+  }
+  if (a < end && __ldg(col + a) == r) {
+    tperm[p] = a;
+  } else {
+    tperm[p] = -1;
+    atomicAdd(missing, 1);
+  }
+}
+
+static int build_segments(tgcn_graph* g, cudaStream_t stream) {
+  std::vector<int> rowptr(g->n_rows + 1);
+  TGCN_CHECK_CUDA(cudaMemcpyAsync(rowptr.data(), g->rowptr, sizeof(int) * (g->n_rows + 1), cudaMemcpyDeviceToHost, stream));
+  TGCN_CHECK_CUDA(cudaStreamSynchronize(stream));
+  TGCN_REQUIRE(rowptr[0] == 0 && (int64_t)rowptr[g->n_rows] == g->nnz, "rowptr does not span [0, nnz]: rowptr[0]=%d rowptr[n]=%d nnz=%lld",
+               rowptr[0], rowptr[g->n_rows], (long long)g->nnz);
+  std::vector<Segment> segs;
+  std::vector<SplitRow> splits;
+  int max_deg = 0;
+  for (int64_t r = 0; r < g->n_rows; ++r) {
+    const int deg = rowptr[r + 1] - rowptr[r];
+    TGCN_REQUIRE(deg >= 0, "rowptr is not non-decreasing at row %lld", (long long)r);
+    if (deg > max_deg) max_deg = deg;
+    if (deg > kSplitThreshold) {
+      SplitRow sr{(int)r, (int)segs.size(), 0, 0};
+      for (int b = rowptr[r]; b < rowptr[r + 1]; b += kSegmentLen) {
+        int e = b + kSegmentLen < rowptr[r + 1] ? b + kSegmentLen : rowptr[r + 1];
+        segs.push_back(Segment{(int)r, b, e, (int)segs.size()});
+        sr.n_parts++;
+      }
+      splits.push_back(sr);
+    }
+  }
+  g->max_degree = max_deg;
+  g->n_segments = (int)segs.size();
+  g->n_split_rows = (int)splits.size();
+  if (!segs.empty()) {
+    TGCN_CHECK_CUDA(cudaMalloc(&g->segments, sizeof(Segment) * segs.size()));
+    TGCN_CHECK_CUDA(cudaMalloc(&g->split_rows, sizeof(SplitRow) * splits.size()));
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(g->segments, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, stream));
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(g->split_rows, splits.data(), sizeof(SplitRow) * splits.size(), cudaMemcpyHostToDevice, stream));
+    TGCN_CHECK_CUDA(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+extern "C" {
+
+int tgcn_abi_version(void) { return TGCN_ABI_VERSION; }
+const char* tgcn_last_error(void) { return tgcn::g_err; }
+
+static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, int64_t row_begin, int64_t n_rows,
+                         int64_t nnz, const int32_t* d_rowptr, const int32_t* d_col, const float* d_val, int is_block,
+                         tgcn_stream_t stream) {
+  TGCN_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  TGCN_REQUIRE(n_users > 0 && n_items > 0 && n_rows > 0 && nnz >= 0, "bad sizes: n_users=%lld n_items=%lld n_rows=%lld nnz=%lld",
+               (long long)n_users, (long long)n_items, (long long)n_rows, (long long)nnz);
+  TGCN_REQUIRE(n_users + n_items < (1ll << 31) && nnz < (1ll << 31), "graph exceeds int32 indexing");
+  TGCN_REQUIRE(d_rowptr && d_col && d_val, "NULL CSR array");
+  int dev_count = 0;
+  TGCN_CHECK_CUDA(cudaGetDeviceCount(&dev_count));
+  TGCN_REQUIRE(dev_count > 0, "no CUDA device: libtgcn_b200 has no CPU fallback");
+  tgcn_graph* g = new tgcn_graph();
+  g->n_users = n_users;
+  g->n_items = n_items;
+  g->row_begin = row_begin;
+  g->n_rows = n_rows;
+  g->nnz = nnz;
+  g->is_block = is_block;
+  g->rowptr = d_rowptr;
+  g->col = d_col;
+  g->val = d_val;
+  g->tperm = nullptr;
+  g->segments = nullptr;
+  g->split_rows = nullptr;
+  g->n_segments = g->n_split_rows = 0;
+  int rc = build_segments(g, (cudaStream_t)stream);
+  if (rc != 0) {
+    tgcn_graph_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return 0;
+}
+
+int tgcn_graph_create(tgcn_graph_t** out, int64_t n_users, int64_t n_items, int64_t nnz, const int32_t* d_rowptr,
+                      const int32_t* d_col, const float* d_val, tgcn_stream_t stream) {
+  return create_common(out, n_users, n_items, 0, n_users + n_items, nnz, d_rowptr, d_col, d_val, 0, stream);
+}
+
+int tgcn_graph_create_block(tgcn_graph_t** out, int64_t n_users, int64_t n_items, int64_t row_begin,
+                            int64_t n_local_rows, int64_t nnz_local, const int32_t* d_rowptr, const int32_t* d_col,
+                            const float* d_val, tgcn_stream_t stream) {
+  return create_common(out, n_users, n_items, row_begin, n_local_rows, nnz_local, d_rowptr, d_col, d_val, 1, stream);
+}
+
+int tgcn_graph_build_transpose_perm(tgcn_graph_t* g, tgcn_stream_t stream) {
+  TGCN_REQUIRE(g != nullptr, "graph is NULL");
+  if (g->tperm) return 0;
+  TGCN_REQUIRE(!g->is_block, "transpose permutation is only defined for a whole-graph handle");
+  if (g->nnz == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int* tperm = nullptr;
+  int* missing = nullptr;
+  TGCN_CHECK_CUDA(cudaMalloc(&tperm, sizeof(int) * g->nnz));
+  TGCN_CHECK_CUDA(cudaMalloc(&missing, sizeof(int)));
+  TGCN_CHECK_CUDA(cudaMemsetAsync(missing, 0, sizeof(int), s));
+  const int threads = 256;
+  const int64_t blocks = (g->nnz + threads - 1) / threads;
+  transpose_perm_kernel<<<(unsigned)blocks, threads, 0, s>>>(g->rowptr, g->col, (int)g->n_rows, g->nnz, tperm, missing);
+  int h_missing = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_missing, missing, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(missing);
+  if (e != cudaSuccess || h_missing != 0) {
+    cudaFree(tperm);
+    if (e != cudaSuccess) set_error("transpose_perm_kernel failed: %s", cudaGetErrorString(e));
+    else set_error("adjacency is not structurally symmetric: %d entries have no transpose partner", h_missing);
+    return 3;
+  }
+  g->tperm = tperm;
+  return 0;
+}
+
+void tgcn_graph_destroy(tgcn_graph_t* g) {
+  if (!g) return;
+  if (g->tperm) cudaFree(g->tperm);
+  if (g->segments) cudaFree(g->segments);
+  if (g->split_rows) cudaFree(g->split_rows);
+  delete g;
+}
+
+int64_t tgcn_graph_num_segments(const tgcn_graph_t* g) { return g ? g->n_segments : -1; }
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// K-layer LightGCN propagation: CSR SpMM with warp-per-row gathers, 128-bit loads, edge-dropout
+// applied as a keep-mask over the static CSR, and the layer-mean fused into the last pass.
+//
+// Roofline: HBM-bound.  Algorithmic bytes per layer = nnz·(4d + 8) + N·4d + (N+1)·4.
+//
+// Work decomposition: one warp per row; the warp's lanes are split into G = 32/LPN groups of LPN
+// lanes, each lane owning VPL float4 of the d-wide row (d = 4·LPN·VPL), so G non-zeros are gathered
+// per step and kBatch non-zeros are in flight per warp.  Rows longer than kSplitThreshold are cut
+// into kSegmentLen-nnz segments handled by separate warps that write partial sums; a tiny second
+// kernel adds the partials in fixed order, so results are deterministic run to run.
+#include "common.cuh"
+
+namespace tgcn {
+
+constexpr int kMaxAddends = TGCN_MAX_LAYERS + 1;
+constexpr int kBatch = 8;  // non-zeros in flight per warp per step
+
+struct Epilogue {
+  int n_add;                          // y = (add[0] + add[1] + ... + acc) / divisor  (+ y_old if accumulate)
+  const float* add_user[kMaxAddends];  // address of row R: R < add_split ? add_user + R·d : add_item + (R - add_split)·d
+  const float* add_item[kMaxAddends];
+  int add_split;
+  float divisor;
+  int accumulate;
+};
+
+struct SpmmArgs {
+  const int* rowptr;
+  const int* col;
+  const float* val;
+  const uint8_t* keep;  // per-nnz keep mask or NULL
+  const int* tperm;     // when set, entry p uses keep[tperm[p]] (transposed dropout matrix)
+  float keep_div;       // survivors are divided by (1 - p)
+  const float* x_user;  // gather source: c < x_split ? x_user + c·d : x_item + (c - x_split)·d
+  const float* x_item;
+  int x_split;
+  int n_rows;
+  int d;
+  const Segment* segments;
+  int n_segments;
+  float* partial;  // (n_segments, d)
+  float* y;        // (n_rows, d)
+  Epilogue ep;
+};
+
+__device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int row, int chunk, float4 acc) {
+  const Epilogue& ep = a.ep;
+  const size_t off = (size_t)chunk * 4;
+  float4 s = acc;
+  if (ep.n_add > 0) {
+    const bool lo = row < ep.add_split;
+    const size_t r = lo ? (size_t)row : (size_t)(row - ep.add_split);
+    s = ldg4((lo ? ep.add_user[0] : ep.add_item[0]) + r * a.d + off);
+    for (int t = 1; t < ep.n_add; ++t) add4(s, ldg4((lo ? ep.add_user[t] : ep.add_item[t]) + r * a.d + off));
+    add4(s, acc);
+  }
+  if (ep.divisor != 1.0f) {
+    s.x /= ep.divisor;
+    s.y /= ep.divisor;
+    s.z /= ep.divisor;
+    s.w /= ep.divisor;
+  }
+  float4* out = reinterpret_cast<float4*>(a.y + (size_t)row * a.d + off);
+  if (ep.accumulate) add4(s, *out);
+  *out = s;
+}
+
+template <int LPN, int VPL>
+__global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
+  constexpr int G = 32 / LPN;
+  constexpr int U = (kBatch / G) > 0 ? (kBatch / G) : 1;
+  const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  int row, begin, end, slot;
+  if (warp < a.n_segments) {
+    const Segment s = a.segments[warp];
+    row = s.row;
+    begin = s.begin;
+    end = s.end;
+    slot = s.slot;
+  } else {
+    row = warp - a.n_segments;
+    if (row >= a.n_rows) return;
+    begin = __ldg(a.rowptr + row);
+    end = __ldg(a.rowptr + row + 1);
+    slot = -1;
+    if (end - begin > kSplitThreshold) return;  // handled as segments
+  }
+  const int grp = lane / LPN, sub = lane % LPN;
+  const int d4 = a.d >> 2;
+  float4 acc[VPL];
+#pragma unroll
+  for (int w = 0; w < VPL; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = begin; base < end; base += 32) {
+    const int p = base + lane;
+    int c = 0;
+    float v = 0.f;
+    bool live = p < end;
+    if (live) {
+      c = __ldg(a.col + p);
+      v = __ldg(a.val + p);
+    }
+    int cnt = min(32, end - base);
+    if (a.keep != nullptr) {
+      if (live) {
+        const int q = a.tperm ? __ldg(a.tperm + p) : p;
+        live = __ldg(a.keep + q) != 0;
+        v = v / a.keep_div;
+      }
+      // compact the surviving entries to the low lanes so no gather slot is wasted
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      cnt = __popc(m);
+      const unsigned src = __fns(m, 0, lane + 1);
+      c = __shfl_sync(0xffffffffu, c, src & 31);
+      v = __shfl_sync(0xffffffffu, v, src & 31);
+    }
+    for (int j = 0; j < cnt; j += G * U) {
+      float4 xs[U][VPL];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = j + u * G + grp;
+        const int cc = __shfl_sync(0xffffffffu, c, idx & 31);
+        vv[u] = __shfl_sync(0xffffffffu, v, idx & 31);
+        const bool ok = idx < cnt;
+        if (!ok) vv[u] = 0.f;
+        const float* xr = (cc < a.x_split ? a.x_user + (size_t)cc * a.d : a.x_item + (size_t)(cc - a.x_split) * a.d);
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) {
+          const int chunk = sub + w * LPN;
+          xs[u][w] = (ok && chunk < d4) ? ldg4(xr + chunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int w = 0; w < VPL; ++w) fma4(acc[w], vv[u], xs[u][w]);
+    }
+  }
+  // combine the G groups
+#pragma unroll
+  for (int o = LPN; o < 32; o <<= 1) {
+#pragma unroll
+    for (int w = 0; w < VPL; ++w) {
+      acc[w].x += __shfl_xor_sync(0xffffffffu, acc[w].x, o);
+      acc[w].y += __shfl_xor_sync(0xffffffffu, acc[w].y, o);
+      acc[w].z += __shfl_xor_sync(0xffffffffu, acc[w].z, o);
+      acc[w].w += __shfl_xor_sync(0xffffffffu, acc[w].w, o);
+    }
+  }
+  if (grp != 0) return;
+#pragma unroll
+  for (int w = 0; w < VPL; ++w) {
+    const int chunk = sub + w * LPN;
+    if (chunk >= d4) continue;
+    if (slot >= 0) *reinterpret_cast<float4*>(a.partial + (size_t)slot * a.d + chunk * 4) = acc[w];
+    else epilogue_store(a, row, chunk, acc[w]);
+  }
+}
+
+// One warp per long row: add its segment partials in order, then the epilogue.
+__global__ void __launch_bounds__(128) spmm_fixup_kernel(const SpmmArgs a, const SplitRow* __restrict__ rows, int n_split) {
+  const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_split) return;
+  const SplitRow sr = rows[warp];
+  const int d4 = a.d >> 2;
+  for (int chunk = lane; chunk < d4; chunk += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int part = 0; part < sr.n_parts; ++part)
+      add4(acc, *reinterpret_cast<const float4*>(a.partial + (size_t)(sr.first_slot + part) * a.d + chunk * 4));
+    epilogue_store(a, sr.row, chunk, acc);
+  }
+}
+
+static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
+  const int64_t warps = (int64_t)a.n_segments + a.n_rows;
+  const int threads = 256;
+  const int64_t blocks = (warps * 32 + threads - 1) / threads;
+  TGCN_REQUIRE(blocks < (1ll << 31), "grid too large");
+  const int d = a.d;
+  if (d <= 16) spmm_rows_kernel<4, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else if (d <= 32) spmm_rows_kernel<8, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else if (d <= 64) spmm_rows_kernel<16, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else if (d <= 128) spmm_rows_kernel<32, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else if (d <= 256) spmm_rows_kernel<32, 2><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else if (d <= 512) spmm_rows_kernel<32, 4><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else TGCN_REQUIRE(false, "embedding width %d > 512 is not supported", d);
+  TGCN_CHECK_LAUNCH();
+  if (g->n_split_rows > 0) {
+    const int fthreads = 128;
+    const int fblocks = (g->n_split_rows * 32 + fthreads - 1) / fthreads;
+    spmm_fixup_kernel<<<fblocks, fthreads, 0, s>>>(a, g->split_rows, g->n_split_rows);
+    TGCN_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static int check_common(const tgcn_graph* g, int64_t d, int32_t n_layers) {
+  TGCN_REQUIRE(g != nullptr, "graph is NULL");
+  TGCN_REQUIRE(d > 0 && d % 4 == 0 && d <= 512, "embedding width d=%lld must be a multiple of 4 and <= 512", (long long)d);
+  TGCN_REQUIRE(n_layers >= 0 && n_layers <= TGCN_MAX_LAYERS, "n_layers=%d out of range [0, %d]", n_layers, TGCN_MAX_LAYERS);
+  return 0;
+}
+
+static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
+  a.rowptr = g->rowptr;
+  a.col = g->col;
+  a.val = g->val;
+  a.keep = nullptr;
+  a.tperm = nullptr;
+  a.keep_div = 1.f;
+  a.n_rows = (int)g->n_rows;
+  a.d = (int)d;
+  a.segments = g->segments;
+  a.n_segments = g->n_segments;
+  a.ep.n_add = 0;
+  a.ep.add_split = g->is_block ? 0x7fffffff : (int)g->n_users;
+  a.ep.divisor = 1.f;
+  a.ep.accumulate = 0;
+  a.x_split = g->is_block ? 0x7fffffff : (int)g->n_users;
+}
+
+}  // namespace tgcn
+
+using namespace tgcn;
+
+extern "C" {
+
+int64_t tgcn_propagate_workspace_bytes(const tgcn_graph_t* g, int64_t d, int32_t n_layers) {
+  if (!g || d <= 0) return -1;
+  const int64_t bufs = n_layers > 1 ? n_layers - 1 : 0;  // fwd keeps E_1..E_{L-1}; bwd ping-pongs within them
+  const int64_t layer = align_up(g->n_rows * d * (int64_t)sizeof(float), 256);
+  return bufs * layer + align_up((int64_t)g->n_segments * d * sizeof(float), 256) + 256;
+}
+
+// Operator-level building block: one SpMM pass with the fused epilogue.  Used by the multi-GPU host
+// code (one call per hop between all-gathers) and by the entry points below.
+int tgcn_spmm_ex(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const float* d_x_item,
+                 const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
+                 const float* const* h_add_user, const float* const* h_add_item, float divisor,
+                 int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream) {
+  if (int rc = check_common(g, d, 1)) return rc;
+  TGCN_REQUIRE(d_x_user && d_y, "NULL x or y");
+  TGCN_REQUIRE(n_add >= 0 && n_add <= kMaxAddends, "n_add=%d out of range", n_add);
+  const int64_t need = align_up((int64_t)g->n_segments * d * sizeof(float), 256);
+  TGCN_REQUIRE(g->n_segments == 0 || (d_workspace && workspace_bytes >= need), "workspace too small: need %lld bytes", (long long)need);
+  SpmmArgs a;
+  base_args(g, d, a);
+  a.x_user = d_x_user;
+  a.x_item = d_x_item ? d_x_item : d_x_user + (size_t)g->n_users * d;
+  if (d_keep) {
+    TGCN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout=%f out of [0,1)", dropout);
+    a.keep = d_keep;
+    a.keep_div = (float)(1.0 - (double)dropout);
+    if (transposed) {
+      TGCN_REQUIRE(g->tperm != nullptr, "transpose permutation not built: call tgcn_graph_build_transpose_perm");
+      a.tperm = g->tperm;
+    }
+  }
+  for (int t = 0; t < n_add; ++t) {
+    a.ep.add_user[t] = h_add_user[t];
+    a.ep.add_item[t] = (h_add_item && h_add_item[t]) ? h_add_item[t] : h_add_user[t] + (size_t)g->n_users * d;
+  }
+  a.ep.n_add = n_add;
+  a.ep.divisor = divisor;
+  a.ep.accumulate = accumulate;
+  a.partial = (float*)d_workspace;
+  a.y = d_y;
+  return launch_spmm(g, a, (cudaStream_t)stream);
+}
+
+int tgcn_spmm_fwd(const tgcn_graph_t* g, int64_t d, const float* d_x, float* d_y, void* d_workspace,
+                  int64_t workspace_bytes, tgcn_stream_t stream) {
+  return tgcn_spmm_ex(g, d, d_x, nullptr, nullptr, 0.f, 0, 0, nullptr, nullptr, 1.f, 0, d_y, d_workspace, workspace_bytes, stream);
+}
+
+int tgcn_propagate_fwd(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* d_user_w,
+                       const float* d_item_w, const uint8_t* d_keep, float dropout, float* d_out, void* d_workspace,
+                       int64_t workspace_bytes, tgcn_stream_t stream) {
+  if (int rc = check_common(g, d, n_layers)) return rc;
+  TGCN_REQUIRE(!g->is_block, "propagate_fwd needs a whole-graph handle; drive row blocks with tgcn_spmm_ex");
+  TGCN_REQUIRE(d_user_w && d_item_w && d_out, "NULL table pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t N = g->n_rows;
+  if (n_layers == 0) {
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(d_out, d_user_w, sizeof(float) * g->n_users * d, cudaMemcpyDeviceToDevice, s));
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(d_out + g->n_users * d, d_item_w, sizeof(float) * g->n_items * d, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const int64_t need = tgcn_propagate_workspace_bytes(g, d, n_layers);
+  TGCN_REQUIRE(workspace_bytes >= need && (d_workspace || need == 0), "workspace too small: need %lld bytes, got %lld", (long long)need, (long long)workspace_bytes);
+  const int64_t layer_bytes = align_up(N * d * (int64_t)sizeof(float), 256);
+  char* ws = (char*)d_workspace;
+  const int n_bufs = n_layers - 1;
+  float* partial = (float*)(ws + (int64_t)n_bufs * layer_bytes);
+  auto buf = [&](int i) { return (float*)(ws + (int64_t)i * layer_bytes); };
+  const float* add_u[kMaxAddends];
+  const float* add_i[kMaxAddends];
+  for (int l = 1; l <= n_layers; ++l) {
+    const bool last = l == n_layers;
+    const float* xu = l == 1 ? d_user_w : buf(l - 2);
+    const float* xi = l == 1 ? d_item_w : nullptr;
+    int n_add = 0;
+    float divisor = 1.f;
+    if (last && !single) {
+      add_u[0] = d_user_w;
+      add_i[0] = d_item_w;
+      for (int t = 1; t < n_layers; ++t) {
+        add_u[t] = buf(t - 1);
+        add_i[t] = nullptr;
+      }
+      n_add = n_layers;
+      divisor = (float)(n_layers + 1);
+    }
+    float* y = last ? d_out : buf(l - 1);
+    if (int rc = tgcn_spmm_ex(g, d, xu, xi, d_keep, dropout, 0, n_add, add_u, add_i, divisor, 0, y, partial,
+                              workspace_bytes - ((char*)partial - ws), stream))
+      return rc;
+  }
+  return 0;
+}
+
+int tgcn_propagate_bwd(tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* d_grad_out,
+                       const uint8_t* d_keep, float dropout, int32_t accumulate, float* d_grad_in, void* d_workspace,
+                       int64_t workspace_bytes, tgcn_stream_t stream) {
+  if (int rc = check_common(g, d, n_layers)) return rc;
+  TGCN_REQUIRE(!g->is_block, "propagate_bwd needs a whole-graph handle");
+  TGCN_REQUIRE(d_grad_out && d_grad_in, "NULL gradient pointer");
+  TGCN_REQUIRE(n_layers >= 1, "propagate_bwd needs n_layers >= 1");
+  const int64_t N = g->n_rows;
+  if (d_keep && !g->tperm) {
+    if (int rc = tgcn_graph_build_transpose_perm(g, stream)) return rc;
+  }
+  const int64_t need = tgcn_propagate_workspace_bytes(g, d, n_layers);
+  TGCN_REQUIRE(workspace_bytes >= need && (d_workspace || need == 0), "workspace too small: need %lld bytes, got %lld", (long long)need, (long long)workspace_bytes);
+  const int64_t layer_bytes = align_up(N * d * (int64_t)sizeof(float), 256);
+  char* ws = (char*)d_workspace;
+  const int n_bufs = n_layers - 1;
+  float* partial = (float*)(ws + (int64_t)n_bufs * layer_bytes);
+  auto buf = [&](int i) { return (float*)(ws + (int64_t)(i & 1) * layer_bytes); };
+  // Horner: H_0 = G;  H_l = G + Â_dropᵀ·H_{l-1};  dE0 = H_L / (L+1).   single: dE0 = (Âᵀ)^L·G.
+  const float* add_u[1] = {d_grad_out};
+  const float* h = d_grad_out;
+  for (int l = 1; l <= n_layers; ++l) {
+    const bool last = l == n_layers;
+    float* y = last ? d_grad_in : buf(l - 1);
+    const int n_add = single ? 0 : 1;
+    const float divisor = (last && !single) ? (float)(n_layers + 1) : 1.f;
+    if (int rc = tgcn_spmm_ex(g, d, h, nullptr, d_keep, dropout, 1, n_add, add_u, nullptr, divisor,
+                              last ? accumulate : 0, y, partial, workspace_bytes - ((char*)partial - ws), stream))
+      return rc;
+    h = y;
+  }
+  return 0;
+}
+
+int tgcn_propagate_host(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* h_user_w,
+                        const float* h_item_w, float* h_out, float* d_stage, void* d_workspace, int64_t workspace_bytes,
+                        tgcn_stream_t stream) {
+  if (int rc = check_common(g, d, n_layers)) return rc;
+  TGCN_REQUIRE(h_user_w && h_item_w && h_out && d_stage, "NULL buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nu = g->n_users * d, ni = g->n_items * d;
+  TGCN_CHECK_CUDA(cudaMemcpyAsync(d_stage, h_user_w, sizeof(float) * nu, cudaMemcpyHostToDevice, s));
+  TGCN_CHECK_CUDA(cudaMemcpyAsync(d_stage + nu, h_item_w, sizeof(float) * ni, cudaMemcpyHostToDevice, s));
+  float* d_out = d_stage + nu + ni;
+  if (int rc = tgcn_propagate_fwd(g, d, n_layers, single, d_stage, d_stage + nu, nullptr, 0.f, d_out, d_workspace, workspace_bytes, stream))
+    return rc;
+  TGCN_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(float) * (nu + ni), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+"""Torch-tensor front end of the C ABI: validates dtype / layout / device on the Python side (the
+library validates sizes), hands raw pointers and the CURRENT torch stream to libtgcn_b200, and owns the
+workspaces.  PyTorch here is plumbing (device memory, streams, autograd glue), not the compute path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str, dims: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.TgcnError(f"{name} must be a CUDA tensor (textgcn_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.TgcnError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.TgcnError(f"{name} must be contiguous")
+    if dims is not None and t.dim() != dims:
+        raise _lib.TgcnError(f"{name} must have {dims} dims, got {t.dim()}")
+    if t.data_ptr() % 16 != 0:
+        raise _lib.TgcnError(f"{name} must be 16-byte aligned")
+    return t
+
+
+def as_index(x, device) -> torch.Tensor:
+    """int32 contiguous device copy of an index list / tensor."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).contiguous()
+    return torch.as_tensor(np.asarray(x), device=device).to(torch.int32).contiguous()
+
+
+class Graph:
+    """Device CSR of Â plus the library handle (segment list, transpose permutation)."""
+
+    def __init__(self, n_users: int, n_items: int, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor,
+                 row_begin: int = 0, block: bool = False):
+        self.lib = _lib.load()
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.rowptr = _chk(rowptr, torch.int32, "rowptr", 1)
+        self.col = _chk(col, torch.int32, "col", 1)
+        self.val = _chk(val, torch.float32, "val", 1)
+        self.nnz = int(col.numel())
+        self.block = bool(block)
+        self.row_begin = int(row_begin)
+        self.n_rows = int(rowptr.numel()) - 1
+        self.device = rowptr.device
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            if block:
+                check(self.lib.tgcn_graph_create_block(ctypes.byref(handle), self.n_users, self.n_items, self.row_begin,
+                                                       self.n_rows, self.nnz, _ptr(self.rowptr), _ptr(self.col),
+                                                       _ptr(self.val), _stream()))
+            else:
+                if self.n_rows != self.n_users + self.n_items:
+                    raise _lib.TgcnError("rowptr must have n_users + n_items + 1 entries")
+                check(self.lib.tgcn_graph_create(ctypes.byref(handle), self.n_users, self.n_items, self.nnz,
+                                                 _ptr(self.rowptr), _ptr(self.col), _ptr(self.val), _stream()))
+        self.handle = handle
+        self._ws = {}
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.tgcn_graph_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    @property
+    def n_nodes(self) -> int:
+        return self.n_users + self.n_items
+
+    @property
+    def n_segments(self) -> int:
+        return int(self.lib.tgcn_graph_num_segments(self.handle))
+
+    @classmethod
+    def from_norm_matrix(cls, norm_matrix: torch.Tensor, n_users: int, n_items: int, device=None) -> "Graph":
+        """From the reference's ``dataset.norm_matrix`` (coalesced COO sorted by (row, col), int64 indices,
+        fp32 values: dataset.py:138, :151-157).  COO order is CSR order, so only rowptr is computed."""
+        device = torch.device(device) if device is not None else norm_matrix.device
+        if device.type != "cuda":
+            raise _lib.TgcnError("Graph needs a CUDA device (textgcn_b200 has no CPU path)")
+        nm = norm_matrix.coalesce()
+        idx = nm.indices()
+        n = n_users + n_items
+        counts = torch.bincount(idx[0], minlength=n)
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=idx.device)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        return cls(n_users, n_items, rowptr.to(device=device, dtype=torch.int32).contiguous(),
+                   idx[1].to(device=device, dtype=torch.int32).contiguous(),
+                   nm.values().to(device=device, dtype=torch.float32).contiguous())
+
+    def workspace(self, d: int, n_layers: int) -> torch.Tensor:
+        """Caller-owned scratch for propagate / spmm (layer buffers + long-row partial sums); grown on demand."""
+        nbytes = max(int(self.lib.tgcn_propagate_workspace_bytes(self.handle, d, n_layers)), 256)
+        ws = self._ws.get("buf")
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws["buf"] = ws
+        return ws
+
+    def build_transpose_perm(self) -> None:
+        with torch.cuda.device(self.device):
+            check(self.lib.tgcn_graph_build_transpose_perm(self.handle, _stream()))
+
+
+def spmm(g: Graph, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """layer_aggregation: Y = Â·X."""
+    _chk(x, torch.float32, "x", 2)
+    d = x.shape[1]
+    out = torch.empty((g.n_rows, d), dtype=torch.float32, device=x.device) if out is None else _chk(out, torch.float32, "out", 2)
+    ws = g.workspace(d, 1)
+    with torch.cuda.device(x.device):
+        check(g.lib.tgcn_spmm_fwd(g.handle, d, _ptr(x), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def spmm_ex(g: Graph, x: torch.Tensor, y: torch.Tensor, addends: Sequence[torch.Tensor] = (), divisor: float = 1.0,
+            keep: Optional[torch.Tensor] = None, dropout: float = 0.0, transposed: bool = False,
+            accumulate: bool = False) -> torch.Tensor:
+    """One SpMM pass with the fused epilogue  y = (Σ addends + Â·x) / divisor  (contiguous operands)."""
+    _chk(x, torch.float32, "x", 2)
+    _chk(y, torch.float32, "y", 2)
+    d = x.shape[1]
+    n = len(addends)
+    arr = (ctypes.c_void_p * max(n, 1))(*[_chk(a, torch.float32, "addend", 2).data_ptr() for a in addends])
+    nul = (ctypes.c_void_p * max(n, 1))()
+    if keep is not None:
+        keep = _keep_u8(keep)
+    ws = g.workspace(d, 1)
+    with torch.cuda.device(x.device):
+        check(g.lib.tgcn_spmm_ex(g.handle, d, _ptr(x), None, _ptr(keep), float(dropout), int(transposed), n, arr, nul,
+                                 float(divisor), int(accumulate), _ptr(y), _ptr(ws), ws.numel(), _stream()))
+    return y
+
+
+def _keep_u8(keep: torch.Tensor) -> torch.Tensor:
+    if keep.dtype == torch.bool:
+        keep = keep.view(torch.uint8)
+    if keep.dtype != torch.uint8 or not keep.is_cuda or not keep.is_contiguous():
+        raise _lib.TgcnError("keep mask must be a contiguous CUDA bool/uint8 tensor of nnz entries")
+    return keep
+
+
+def propagate_fwd(g: Graph, user_w: torch.Tensor, item_w: torch.Tensor, n_layers: int, single: bool = False,
+                  keep: Optional[torch.Tensor] = None, dropout: float = 0.0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """representation: (N, d) result; rows [0, n_users) are users_emb."""
+    _chk(user_w, torch.float32, "user_w", 2)
+    _chk(item_w, torch.float32, "item_w", 2)
+    d = user_w.shape[1]
+    if user_w.shape[0] != g.n_users or item_w.shape != (g.n_items, d):
+        raise _lib.TgcnError("embedding tables do not match the graph")
+    if keep is not None:
+        keep = _keep_u8(keep)
+        if keep.numel() != g.nnz:
+            raise _lib.TgcnError("keep mask must have nnz entries")
+    out = torch.empty((g.n_nodes, d), dtype=torch.float32, device=user_w.device) if out is None else _chk(out, torch.float32, "out", 2)
+    ws = g.workspace(d, n_layers)
+    with torch.cuda.device(user_w.device):
+        check(g.lib.tgcn_propagate_fwd(g.handle, d, n_layers, int(single), _ptr(user_w), _ptr(item_w), _ptr(keep),
+                                       float(dropout), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def propagate_bwd(g: Graph, grad_out: torch.Tensor, n_layers: int, single: bool = False,
+                  keep: Optional[torch.Tensor] = None, dropout: float = 0.0,
+                  grad_in: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _chk(grad_out, torch.float32, "grad_out", 2)
+    d = grad_out.shape[1]
+    if keep is not None:
+        keep = _keep_u8(keep)
+    if grad_in is None:
+        grad_in = torch.empty_like(grad_out)
+        accumulate = False
+    _chk(grad_in, torch.float32, "grad_in", 2)
+    ws = g.workspace(d, n_layers)
+    with torch.cuda.device(grad_out.device):
+        check(g.lib.tgcn_propagate_bwd(g.handle, d, n_layers, int(single), _ptr(grad_out), _ptr(keep), float(dropout),
+                                       int(accumulate), _ptr(grad_in), _ptr(ws), ws.numel(), _stream()))
+    return grad_in
+
+
+def bpr_fwd_bwd(n_users: int, n_items: int, emb: torch.Tensor, user_w: torch.Tensor, item_w: torch.Tensor,
+                users: torch.Tensor, pos: torch.Tensor, negs: torch.Tensor, reg_lambda: float,
+                grad_emb: Optional[torch.Tensor], grad_w0: Optional[torch.Tensor]) -> torch.Tensor:
+    """Fused BPR(SELU)+L2 step.  negs is (n_neg, batch) int32.  Returns losses = [bpr, reg] (device)."""
+    lib = _lib.load()
+    _chk(emb, torch.float32, "emb", 2)
+    d = emb.shape[1]
+    users, pos, negs = (_chk(t, torch.int32, n) for t, n in ((users, "users"), (pos, "pos"), (negs, "negs")))
+    batch = users.numel()
+    n_neg = negs.numel() // batch
+    losses = torch.empty(2, dtype=torch.float32, device=emb.device)
+    ws = torch.empty(int(lib.tgcn_bpr_workspace_bytes(batch)), dtype=torch.uint8, device=emb.device)
+    with torch.cuda.device(emb.device):
+        check(lib.tgcn_bpr_fwd_bwd(n_users, n_items, d, batch, n_neg, _ptr(users), _ptr(pos), _ptr(negs), _ptr(emb),
+                                   _ptr(user_w), _ptr(item_w), float(reg_lambda), _ptr(losses), _ptr(grad_emb),
+                                   _ptr(grad_w0), _ptr(ws), ws.numel(), _stream()))
+    return losses
+
+
+def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: torch.Tensor, k: int,
+              users: Optional[torch.Tensor] = None, n_rank: Optional[int] = None,
+              item_range: Optional[Tuple[int, int]] = None, user_bias: Optional[torch.Tensor] = None,
+              item_bias: Optional[torch.Tensor] = None, finalize: bool = True, by_position: bool = False
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused score + mask + top-k.  Returns (ids (n_rank, k) int32, scores (n_rank, k) fp32).
+
+    ``users`` (int32 ids) selects the rows to rank and whose train items are masked; with ``by_position`` the
+    user vectors / bias are already packed in list order (row m belongs to users[m])."""
+    lib = _lib.load()
+    _chk(user_vecs, torch.float32, "user_vecs", 2)
+    _chk(item_vecs, torch.float32, "item_vecs", 2)
+    K = user_vecs.shape[1]
+    if item_vecs.shape[1] != K:
+        raise _lib.TgcnError("user and item vectors differ in width")
+    if users is not None:
+        users = _chk(users, torch.int32, "users", 1)
+        n_rank = users.numel()
+    elif n_rank is None:
+        n_rank = user_vecs.shape[0]
+    i0, i1 = item_range if item_range is not None else (0, item_vecs.shape[0])
+    dev = user_vecs.device
+    ids = torch.empty((n_rank, k), dtype=torch.int32, device=dev)
+    scores = torch.empty((n_rank, k), dtype=torch.float32, device=dev)
+    nbytes = int(lib.tgcn_eval_workspace_bytes(n_rank, i1 - i0, k))
+    if nbytes < 0:
+        raise _lib.TgcnError("bad eval shape")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tgcn_eval_topk(mask_graph.handle if mask_graph is not None else None, n_rank, _ptr(users),
+                                 _ptr(user_vecs), user_vecs.stride(0), _ptr(item_vecs), item_vecs.stride(0), K, i0, i1,
+                                 _ptr(user_bias), _ptr(item_bias), int(by_position), k, int(finalize), _ptr(ids), _ptr(scores),
+                                 _ptr(ws), ws.numel(), _stream()))
+    return ids, scores
+
+
+def topk_merge(mask_graph: Optional[Graph], part_ids: torch.Tensor, part_scores: torch.Tensor,
+               users: Optional[torch.Tensor] = None, finalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge (n_parts, n_rows, k) partial top-k tables."""
+    lib = _lib.load()
+    _chk(part_ids, torch.int32, "part_ids", 3)
+    _chk(part_scores, torch.float32, "part_scores", 3)
+    n_parts, n_rows, k = part_ids.shape
+    ids = torch.empty((n_rows, k), dtype=torch.int32, device=part_ids.device)
+    scores = torch.empty((n_rows, k), dtype=torch.float32, device=part_ids.device)
+    with torch.cuda.device(part_ids.device):
+        check(lib.tgcn_topk_merge(mask_graph.handle if mask_graph is not None else None, n_rows, _ptr(users), n_parts, k,
+                                  _ptr(part_ids), _ptr(part_scores), int(finalize), _ptr(ids), _ptr(scores), _stream()))
+    return ids, scores
+
+
+def adv_select(g: Graph, emb: torch.Tensor, users: torch.Tensor, cands: torch.Tensor, kmax: int,
+               want_scores: bool = False):
+    """Hardest-negative selection.  Returns (negs (B, kmax) int32 -1 padded, counts (B,), scores or None)."""
+    _chk(emb, torch.float32, "emb", 2)
+    users = _chk(users, torch.int32, "users", 1)
+    cands = _chk(cands, torch.int32, "cands", 2)
+    b, c = cands.shape
+    negs = torch.empty((b, kmax), dtype=torch.int32, device=emb.device)
+    counts = torch.empty(b, dtype=torch.int32, device=emb.device)
+    scores = torch.empty((b, c), dtype=torch.float32, device=emb.device) if want_scores else None
+    with torch.cuda.device(emb.device):
+        check(g.lib.tgcn_adv_select(g.handle, emb.shape[1], b, c, _ptr(users), _ptr(cands), _ptr(emb), kmax, _ptr(negs),
+                                    _ptr(counts), _ptr(scores), _stream()))
+    return negs, counts, scores
+
+
+def ltr_pairwise_features(n_users: int, emb, users, items, users_rev, users_desc, items_rev, items_desc,
+                          pop_users=None, pop_items=None) -> torch.Tensor:
+    lib = _lib.load()
+    n_feat = 7 if pop_users is not None else 5
+    b = users.numel()
+    out = torch.empty((b, n_feat), dtype=torch.float32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        check(lib.tgcn_ltr_pairwise_features(n_users, emb.shape[1], users_rev.shape[1], b, n_feat,
+                                             _ptr(_chk(users, torch.int32, "users")), _ptr(_chk(items, torch.int32, "items")),
+                                             _ptr(_chk(emb, torch.float32, "emb")), _ptr(_chk(users_rev, torch.float32, "users_rev")),
+                                             _ptr(_chk(users_desc, torch.float32, "users_desc")),
+                                             _ptr(_chk(items_rev, torch.float32, "items_rev")),
+                                             _ptr(_chk(items_desc, torch.float32, "items_desc")),
+                                             _ptr(pop_users), _ptr(pop_items), _ptr(out), _stream()))
+    return out
+
+
+def ltr_pairwise_emb_bwd(n_users: int, emb, users, items, gf0, grad_emb) -> None:
+    lib = _lib.load()
+    with torch.cuda.device(emb.device):
+        check(lib.tgcn_ltr_pairwise_emb_bwd(n_users, emb.shape[1], users.numel(), _ptr(users), _ptr(items), _ptr(emb),
+                                            _ptr(_chk(gf0, torch.float32, "gf0")), _ptr(grad_emb), _stream()))
+
+
+def ltr_pack_items(items_emb, items_rev, items_desc, w5: Sequence[float]) -> torch.Tensor:
+    lib = _lib.load()
+    n, d = items_emb.shape
+    D = items_rev.shape[1]
+    out = torch.empty((n, d + 2 * D), dtype=torch.float32, device=items_emb.device)
+    w = (ctypes.c_float * 5)(*[float(x) for x in w5])
+    with torch.cuda.device(items_emb.device):
+        check(lib.tgcn_ltr_pack_items(n, d, D, _ptr(_chk(items_emb, torch.float32, "items_emb")),
+                                      _ptr(_chk(items_rev, torch.float32, "items_rev")),
+                                      _ptr(_chk(items_desc, torch.float32, "items_desc")), w, _ptr(out), _stream()))
+    return out
+
+
+def ltr_pack_users(users: Optional[torch.Tensor], users_emb, users_rev, users_desc) -> torch.Tensor:
+    lib = _lib.load()
+    d, D = users_emb.shape[1], users_rev.shape[1]
+    n = users.numel() if users is not None else users_emb.shape[0]
+    out = torch.empty((n, d + 2 * D), dtype=torch.float32, device=users_emb.device)
+    with torch.cuda.device(users_emb.device):
+        check(lib.tgcn_ltr_pack_users(n, _ptr(users), d, D, _ptr(_chk(users_emb, torch.float32, "users_emb")),
+                                      _ptr(_chk(users_rev, torch.float32, "users_rev")),
+                                      _ptr(_chk(users_desc, torch.float32, "users_desc")), _ptr(out), _stream()))
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step) -> None:
+    lib = _lib.load()
+    with torch.cuda.device(p.device):
+        check(lib.tgcn_adam_step(p.numel(), _ptr(p), _ptr(_chk(g, torch.float32, "grad")), _ptr(m), _ptr(v), lr, beta1,
+                                 beta2, eps, step, _stream()))

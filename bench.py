@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the LightGCN hot path (BASELINE.json metric: propagation edges/s + eval users/s, top-k@20).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one pass of the hot path over the whole graph: ``representation`` = L fused SpMM layers + layer mean.
+``value`` = nnz(Â)·L / t with inputs resident in HBM; ``e2e`` = the same through the host-buffer C-ABI call
+(``tgcn_propagate_host``: H2D of E0, L layers, D2H of the result).  Workloads (``config.workload``):
+  N = 1 : "c2" — BASELINE.json configs[1], Electronics-shaped (190k users, 63k items, 1.7M edges, d 64, 3 layers)
+  N > 1 : "c5" — configs[4] (10M users, 2M items, 200M edges, d 128, 4 layers), STRONG scaling: Â row-partitioned
+          by nnz, NCCL all-gather of layer embeddings between hops, item-sharded eval with cross-GPU top-k merge.
+Between timed iterations L2 is flushed (a 256 MiB write); timing is CUDA events on the launching stream, max over
+ranks.  The JSON line also carries ``roofline`` (dominant kernel: spmm_rows_kernel, HBM bound), ``cpu_baseline``
+(oracle port on the host cores, N = 1 only), ``eval`` (users/s) and ``clocks``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "propagation edges/s (directed nnz x layers per second; eval users/s top-k@20 in `eval`)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c5", "tiny"])
+    ap.add_argument("--eval-users", type=int, default=0, help="users ranked in the eval leg (0 = workload default)")
+    ap.add_argument("--eval-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--topk", type=int, default=20)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def spmm_layer_bytes(nnz, n, d):
+    """Algorithmic bytes of one SpMM layer: gathered rows + col/val + output rows + rowptr."""
+    return nnz * (4 * d + 8) + n * 4 * d + (n + 1) * 4
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def build_workload(name, device):
+    import torch
+    from textgcn_b200.graph import norm_adj_csr
+    from textgcn_b200.synthetic import WORKLOADS, interactions
+    nu, ni, ne, d, L = WORKLOADS[name]
+    tu, ti = interactions(nu, ni, ne, device, seed=0)
+    rowptr, col, val = norm_adj_csr(tu, ti, nu, ni)
+    del tu, ti
+    torch.manual_seed(0)
+    gen = torch.Generator(device=device).manual_seed(0)
+    uw = torch.randn(nu, d, generator=gen, device=device) * 0.1  # base_model.py:68-69
+    iw = torch.randn(ni, d, generator=gen, device=device) * 0.1
+    return dict(name=name, nu=nu, ni=ni, ne=ne, d=d, L=L, rowptr=rowptr.contiguous(), col=col.contiguous(),
+                val=val.contiguous(), uw=uw, iw=iw, nnz=int(col.numel()))
+
+
+def timed_steps(fn, steps, warmup, flush, torch):
+    """W untimed + K timed calls; L2 flushed (untimed) before every timed call; per-step CUDA events."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in ev]
+
+
+def cpu_baseline(w, topk, n_predict=2048):
+    """The reference's CPU path (oracle port: torch.sparse.mm x L + mean; matmul + mask + topk) on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import lightgcn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = w["nu"] + w["ni"]
+    rowptr = w["rowptr"].cpu().to(torch.int64)
+    row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    norm = torch.sparse_coo_tensor(torch.stack([row, w["col"].cpu().to(torch.int64)]), w["val"].cpu(), (n, n)).coalesce()
+    uw, iw = w["uw"].cpu(), w["iw"].cpu()
+    best = float("inf")
+    for _ in range(3):
+        t = time.perf_counter()
+        ue, ie = O.propagate(norm, uw, iw, w["L"])
+        best = min(best, time.perf_counter() - t)
+    users = np.arange(min(n_predict, w["nu"]))
+    col = w["col"].cpu().numpy().astype(np.int64) - w["nu"]
+    rp = rowptr.numpy()
+    train_lists = [col[rp[u]:rp[u + 1]] for u in users]
+    t = time.perf_counter()
+    O.predict_topk_torch(ue, ie, users, train_lists, topk)
+    t_pred = time.perf_counter() - t
+    return {"value": w["nnz"] * w["L"] / best, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": f"full {w['name']} representation ({w['L']} x torch.sparse.mm + mean), best of 3 = {best * 1e3:.1f} ms; "
+                      f"predict on {len(users)} users = {t_pred * 1e3:.1f} ms",
+            "eval_users_per_s": len(users) / t_pred, "ms_per_step": best * 1e3}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    import torch
+    name = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c5")
+    dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+    from textgcn_b200.synthetic import WORKLOADS
+    from oracle import lightgcn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = build_workload(name, dev)
+    n = w["nu"] + w["ni"]
+    rowptr = w["rowptr"].cpu().to(torch.int64)
+    # bounded sample: a leading row block of Â holding <= 8M non-zeros (the whole graph at c2)
+    max_nnz = 8_000_000
+    rows = n if w["nnz"] <= max_nnz else int(torch.searchsorted(rowptr, torch.tensor(max_nnz)).item())
+    nnz_s = int(rowptr[rows])
+    row = torch.repeat_interleave(torch.arange(rows), rowptr[1:rows + 1] - rowptr[:rows])
+    block = torch.sparse_coo_tensor(torch.stack([row, w["col"][:nnz_s].cpu().to(torch.int64)]), w["val"][:nnz_s].cpu(),
+                                    (rows, n)).coalesce()
+    e0 = torch.cat([w["uw"].cpu(), w["iw"].cpu()])
+    full = rows == n
+
+    def step():
+        if full:
+            return O.propagate(block, w["uw"].cpu(), w["iw"].cpu(), w["L"])
+        outs = [torch.sparse.mm(block, e0) for _ in range(w["L"])]  # L row-block SpMMs (same work per layer)
+        return torch.mean(torch.stack([e0[:rows]] + outs), dim=0)
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    times = []
+    budget = time.perf_counter() + 150
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t)
+        if time.perf_counter() > budget:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    value = nnz_s * w["L"] / (ms * 1e-3)
+    sample = (f"{'full' if full else 'leading row block of'} {name}: {rows} rows, {nnz_s} nnz, {w['L']} layers, "
+              f"{len(times)} steps of torch.sparse.mm on {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "n_users": w["nu"], "n_items": w["ni"], "nnz": w["nnz"], "emb": w["d"], "layers": w["L"]},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from textgcn_b200 import ops
+    from textgcn_b200 import dist as tdist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    name = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c5")
+    w = build_workload(name, dev)
+    nu, ni, d, L, nnz = w["nu"], w["ni"], w["d"], w["L"], w["nnz"]
+    n = nu + ni
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm_peak, peak_src = peaks()
+    sampler = ClockSampler(local_rank)
+
+    step_bytes = L * spmm_layer_bytes(nnz, n, d) + L * n * 4 * d  # + mean epilogue reads of E0..E_{L-1}
+    extra = {}
+    if world == 1:
+        graph = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
+        out = torch.empty((n, d), dtype=torch.float32, device=dev)
+
+        def step():
+            ops.propagate_fwd(graph, w["uw"], w["iw"], L, out=out)
+
+        sampler.start()
+        times = timed_steps(step, args.steps, args.warmup, flush, torch)
+        launches_per_step = L * (2 if graph.n_segments > 0 else 1)
+        parallelism = "single GPU"
+        scaling = "weak"
+    else:
+        part = tdist.RowPartition(w["rowptr"], world)
+        rp, col, val = part.local_block(rank, w["rowptr"], w["col"], w["val"])
+        s, e = part.rows(rank)
+        lgraph = ops.Graph(nu, ni, rp, col, val, row_begin=s, block=True)
+        prop = tdist.DistPropagator(part, rank, lgraph, d, L, dev)
+        e0 = torch.cat([w["uw"], w["iw"]])[s:e].contiguous()
+        out_local = torch.empty((e - s, d), dtype=torch.float32, device=dev)
+
+        def step():
+            prop.propagate(e0, out_local)
+
+        dist.barrier()
+        sampler.start()
+        times = timed_steps(step, args.steps, args.warmup, flush, torch)
+        dist.barrier()
+        launches_per_step = L * (2 if lgraph.n_segments > 0 else 1)
+        parallelism = f"row-block x{world}, NCCL all-gather between hops"
+        scaling = "strong"
+        extra["comm_bytes_per_hop_per_rank"] = prop.comm_bytes_per_hop
+    torch.cuda.synchronize()
+    total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms) / args.steps
+    value = nnz * L / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI entry (N = 1) / host-staged shard (N > 1) -------------------------
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            h_u = torch.empty((nu, d), dtype=torch.float32).pin_memory().copy_(w["uw"].cpu())
+            h_i = torch.empty((ni, d), dtype=torch.float32).pin_memory().copy_(w["iw"].cpu())
+            h_o = torch.empty((n, d), dtype=torch.float32).pin_memory()
+            stage = torch.empty((2 * n, d), dtype=torch.float32, device=dev)
+
+            def e2e_step():
+                ops.propagate_host(graph, h_u, h_i, h_o, L, stage)
+        else:
+            h_e0 = torch.empty_like(e0, device="cpu").pin_memory().copy_(e0.cpu())
+            h_o = torch.empty_like(out_local, device="cpu").pin_memory()
+            d_e0 = torch.empty_like(e0)
+
+            def e2e_step():
+                d_e0.copy_(h_e0, non_blocking=True)
+                prop.propagate(d_e0, out_local)
+                h_o.copy_(out_local, non_blocking=True)
+        if world > 1:
+            dist.barrier()
+        et = timed_steps(e2e_step, max(3, args.steps // 2), 2, flush, torch)
+        e_ms = torch.tensor([sum(et) / len(et)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        rows_local = n if world == 1 else (e - s)
+        e2e = {"value": nnz * L / (float(e_ms) * 1e-3), "unit": "edges/s", "ms_per_step": float(e_ms),
+               "h2d_bytes_per_step": rows_local * d * 4, "d2h_bytes_per_step": rows_local * d * 4,
+               "api": "tgcn_propagate_host (pinned host E0 -> device, L layers, result -> pinned host)" if world == 1
+               else "host-pinned E0 shard -> device, L hops with all-gather, result shard -> host"}
+
+    # ---- eval leg: fused score + mask + top-k ----------------------------------------------------------------
+    ev = None
+    if not args.no_eval:
+        k = args.topk
+        if world == 1:
+            emb = out
+            n_eval = args.eval_users or (nu if name != "c5" else 16384)
+            users = torch.arange(n_eval, dtype=torch.int32, device=dev)
+            h_users = torch.arange(n_eval, dtype=torch.int32).pin_memory()
+            h_ids = torch.empty((n_eval, k), dtype=torch.int32).pin_memory()
+            h_sc = torch.empty((n_eval, k), dtype=torch.float32).pin_memory()
+
+            def eval_step():
+                return ops.eval_topk(graph, emb[:nu], emb[nu:], k, users=users)
+
+            def eval_e2e():
+                du = h_users.to(dev, non_blocking=True)
+                ids, sc = ops.eval_topk(graph, emb[:nu], emb[nu:], k, users=du)
+                h_ids.copy_(ids, non_blocking=True)
+                h_sc.copy_(sc, non_blocking=True)
+        else:
+            full = prop.gather_full(out_local)
+            mask_rows = int(w["rowptr"][nu])
+            mgraph = ops.Graph(nu, ni, w["rowptr"][:nu + 1].contiguous(), w["col"][:mask_rows].contiguous(),
+                               w["val"][:mask_rows].contiguous(), row_begin=0, block=True)
+            n_eval = args.eval_users or 16384 * world
+            n_eval = (n_eval + world - 1) // world * world
+            users = torch.arange(n_eval, dtype=torch.int32, device=dev)
+
+            def eval_step():
+                return tdist.sharded_eval_topk(mgraph, full[:nu], full[nu:], users, k, rank, world)
+
+            eval_e2e = None
+        t_ev = timed_steps(eval_step, args.eval_steps, 1, flush, torch)
+        ev_ms = torch.tensor([sum(t_ev) / len(t_ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ev_ms, op=dist.ReduceOp.MAX)
+        ev = {"users_per_s": n_eval / (float(ev_ms) * 1e-3), "k": k, "n_users_ranked": n_eval, "n_items": ni,
+              "ms": float(ev_ms), "score_flops_per_s": 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
+              "kernel": "eval_topk_simt_kernel (exact fp32 FMA) + topk_merge_kernel",
+              "sharding": "single GPU" if world == 1 else f"item range x{world}, all-to-all + merge"}
+        if eval_e2e is not None:
+            t_e = timed_steps(eval_e2e, args.eval_steps, 1, flush, torch)
+            ev["e2e_users_per_s"] = n_eval / (sum(t_e) / len(t_e) * 1e-3)
+            ev["e2e_h2d_bytes"] = n_eval * 4
+            ev["e2e_d2h_bytes"] = n_eval * k * 8
+    sampler.stop_flag = True
+    sampler.join(timeout=1)
+
+    # ---- same workload on ONE GPU, measured by rank 0 in the same run (for honest strong-scaling ratios) ----
+    if world > 1 and rank == 0:
+        try:
+            g1 = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
+            out1 = torch.empty((n, d), dtype=torch.float32, device=dev)
+            t1 = timed_steps(lambda: ops.propagate_fwd(g1, w["uw"], w["iw"], L, out=out1), max(2, args.steps // 4), 1, flush, torch)
+            extra["n1_same_workload"] = {"value": nnz * L / (sum(t1) / len(t1) * 1e-3), "ms_per_step": sum(t1) / len(t1)}
+            del g1, out1
+        except Exception as exc:  # e.g. out of memory on a shared device
+            extra["n1_same_workload"] = {"error": str(exc)[:200]}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        per_rank_bytes = step_bytes / world
+        achieved = per_rank_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(name)
+        line = {
+            "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": name, "n_users": nu, "n_items": ni, "train_interactions": w["ne"], "nnz": nnz, "emb": d,
+                       "layers": L, "parallelism": parallelism, "l2": "flushed between timed iterations (256 MiB write)",
+                       "interactions_per_s": value / 2},
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "kernel": "spmm_rows_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": step_bytes, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "per_gpu": world > 1},
+            "eval": ev, "clocks": sampler.summary(),
+        }
+        line.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w, args.topk)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

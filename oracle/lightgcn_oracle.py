@@ -223,6 +223,25 @@ def predict_topk(users_emb: torch.Tensor, items_emb: torch.Tensor, users: Sequen
     return ids, sc.numpy()
 
 
+def predict_topk_torch(users_emb: torch.Tensor, items_emb: torch.Tensor, users: Sequence[int],
+                       train_lists: Sequence[Sequence[int]], k: int, batch_size: int = 2048):
+    """The reference's predict loop verbatim in its op sequence (matmul, index_put -inf, torch.topk, round; base_model.py
+    :255-263) — used as the timed CPU baseline; tie order is torch.topk's, so parity checks use ``predict_topk``."""
+    users = np.asarray(users, dtype=np.int64)
+    y_pred, y_probs = [], []
+    for j in range(0, len(users), batch_size):
+        bu = users[j:j + batch_size]
+        tu = torch.from_numpy(bu)
+        rating = torch.matmul(users_emb[tu], items_emb.t())
+        rows = np.concatenate([np.full(len(train_lists[r + j]), r, dtype=np.int64) for r in range(len(bu))])
+        cols = np.concatenate([np.asarray(train_lists[r + j], dtype=np.int64) for r in range(len(bu))])
+        rating[torch.from_numpy(rows), torch.from_numpy(cols)] = -np.inf
+        probs, rank_indices = torch.topk(rating, k=k)
+        y_pred.append(rank_indices)
+        y_probs.append(probs.round(decimals=4))
+    return torch.cat(y_pred).numpy(), torch.cat(y_probs).numpy()
+
+
 def canonicalize_lists(ids: np.ndarray, scores: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """Re-order each already-selected top-k row to (score desc, id asc)."""
     ids = np.asarray(ids).copy()

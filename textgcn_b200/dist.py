@@ -1,0 +1,165 @@
+"""Multi-GPU hot path on one NVSwitch box: one process per GPU, torch.distributed (NCCL) for the plumbing.
+
+Propagation: Â is partitioned by ROW BLOCK, balanced by nnz.  Rank p owns rows [starts[p], starts[p+1]) and the
+matching rows of every layer's embedding table.  One hop = all-gather of the P row blocks (padded to a common
+``max_rows`` so the collective is a single contiguous ``all_gather_into_tensor``) followed by the local SpMM,
+whose column indices were relabelled once, at partition time, to index the padded gathered table directly.  The
+layer mean is local (fused into the last SpMM's epilogue).
+
+Evaluation: sharded by ITEM range (north_star).  Every rank ranks all requested users against its item shard
+with the fused score+mask+top-k kernel, the (U, k) partial tables are exchanged with an all-to-all so that rank p
+receives every shard's candidates for user slice p, and ``tgcn_topk_merge`` reduces P·k -> k under the same strict
+order; the result is sharded by user slice (``gather=True`` all-gathers it).
+
+The compute calls are injected (``spmm_fn`` / ``rank_fn`` / ``merge_fn``) so the partition / relabel / exchange
+logic is unit-tested with world_size-2 gloo on CPU; the defaults are the CUDA kernels and nothing else.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def nnz_balanced_starts(rowptr: torch.Tensor, world_size: int) -> List[int]:
+    """Row cut points s_0=0 < ... < s_P=N such that every block holds ~nnz/P non-zeros."""
+    n = rowptr.numel() - 1
+    nnz = int(rowptr[-1])
+    targets = torch.tensor([nnz * p // world_size for p in range(1, world_size)], dtype=rowptr.dtype, device=rowptr.device)
+    cuts = torch.searchsorted(rowptr.contiguous(), targets, right=False).tolist() if world_size > 1 else []
+    starts = [0] + [min(max(int(c), 0), n) for c in cuts] + [n]
+    for i in range(1, len(starts)):  # keep monotone (degenerate tiny graphs)
+        starts[i] = max(starts[i], starts[i - 1])
+    return starts
+
+
+class RowPartition:
+    """Row-block partition of the CSR of Â and the padded-table relabelling of its columns."""
+
+    def __init__(self, rowptr: torch.Tensor, world_size: int):
+        self.world_size = world_size
+        self.starts = nnz_balanced_starts(rowptr, world_size)
+        self.n_rows = rowptr.numel() - 1
+        self.max_rows = max(self.starts[p + 1] - self.starts[p] for p in range(world_size))
+        # 16-byte alignment of every block start for any d % 4 == 0 is automatic (rows are whole)
+
+    def rows(self, rank: int) -> Tuple[int, int]:
+        return self.starts[rank], self.starts[rank + 1]
+
+    def owner(self, idx: torch.Tensor) -> torch.Tensor:
+        bounds = torch.tensor(self.starts[1:], device=idx.device, dtype=idx.dtype)
+        return torch.searchsorted(bounds, idx, right=True)
+
+    def relabel(self, col: torch.Tensor) -> torch.Tensor:
+        """Global row id -> row of the (P·max_rows, d) gathered table."""
+        own = self.owner(col.to(torch.int64))
+        starts = torch.tensor(self.starts[:-1], device=col.device, dtype=torch.int64)
+        return (own * self.max_rows + (col.to(torch.int64) - starts[own])).to(torch.int32)
+
+    def local_block(self, rank: int, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor):
+        """(rowptr_local, col_relabelled, val_local) of rank's row block."""
+        s, e = self.rows(rank)
+        lo, hi = int(rowptr[s]), int(rowptr[e])
+        rp = (rowptr[s:e + 1] - rowptr[s]).to(torch.int32).contiguous()
+        return rp, self.relabel(col[lo:hi]).contiguous(), val[lo:hi].contiguous()
+
+
+def _default_spmm(graph, x, y, addends, divisor):
+    from . import ops
+    return ops.spmm_ex(graph, x, y, addends=addends, divisor=divisor)
+
+
+class DistPropagator:
+    """K-layer propagation over a row-partitioned Â with an all-gather of layer embeddings between hops."""
+
+    def __init__(self, part: RowPartition, rank: int, local_graph, d: int, n_layers: int, device,
+                 group=None, spmm_fn: Callable = _default_spmm):
+        self.part, self.rank, self.graph, self.d, self.n_layers = part, rank, local_graph, d, n_layers
+        self.group, self.spmm_fn = group, spmm_fn
+        self.n_local = part.starts[rank + 1] - part.starts[rank]
+        P, mr = part.world_size, part.max_rows
+        self.gathered = torch.zeros((P * mr, d), dtype=torch.float32, device=device)
+        # layer buffers are max_rows tall so they can be handed to the collective without a pad copy
+        self.bufs = [torch.zeros((mr, d), dtype=torch.float32, device=device) for _ in range(max(n_layers, 1))]
+        self.comm_bytes_per_hop = (P - 1) * mr * d * 4  # received per rank
+
+    def all_gather(self, block: torch.Tensor) -> torch.Tensor:
+        dist.all_gather_into_tensor(self.gathered, block, group=self.group)
+        return self.gathered
+
+    def propagate(self, e0_local: torch.Tensor, out_local: Optional[torch.Tensor] = None, single: bool = False
+                  ) -> torch.Tensor:
+        """e0_local: this rank's rows of E0 (n_local, d).  Returns this rank's rows of the layer mean."""
+        n, L = self.n_local, self.n_layers
+        self.bufs[0][:n].copy_(e0_local)
+        if out_local is None:
+            out_local = torch.empty((n, self.d), dtype=torch.float32, device=e0_local.device)
+        cur = self.bufs[0]
+        for layer in range(1, L + 1):
+            table = self.all_gather(cur)
+            last = layer == L
+            if last:
+                addends = [] if single else [self.bufs[t][:n] for t in range(L)]
+                self.spmm_fn(self.graph, table, out_local, addends, 1.0 if single else float(L + 1))
+            else:
+                y = self.bufs[layer]
+                self.spmm_fn(self.graph, table, y[:n], [], 1.0)
+                cur = y
+        return out_local
+
+    def gather_full(self, local: torch.Tensor) -> torch.Tensor:
+        """All-gather local rows of a table and strip the padding -> (N, d) on every rank."""
+        n = self.n_local
+        self.bufs[0][:n].copy_(local)
+        table = self.all_gather(self.bufs[0])
+        mr = self.part.max_rows
+        return torch.cat([table[p * mr: p * mr + (self.part.starts[p + 1] - self.part.starts[p])]
+                          for p in range(self.part.world_size)])
+
+
+def item_shard(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    per = (n_items + world_size - 1) // world_size
+    return min(rank * per, n_items), min((rank + 1) * per, n_items)
+
+
+def _default_rank(mask_graph, user_vecs, item_vecs, k, users, item_range):
+    from . import ops
+    return ops.eval_topk(mask_graph, user_vecs, item_vecs, k, users=users, item_range=item_range, finalize=False)
+
+
+def _default_merge(mask_graph, part_ids, part_scores, users):
+    from . import ops
+    return ops.topk_merge(mask_graph, part_ids, part_scores, users=users, finalize=True)
+
+
+def sharded_eval_topk(mask_graph, user_vecs: torch.Tensor, item_vecs: torch.Tensor, users: torch.Tensor, k: int,
+                      rank: int, world_size: int, group=None, gather: bool = False,
+                      rank_fn: Callable = _default_rank, merge_fn: Callable = _default_merge):
+    """Item-sharded full ranking with a cross-GPU top-k merge.
+
+    ``users`` (int32 ids, identical on every rank; its length must be a multiple of world_size) are ranked by every
+    rank against its own item range; partial (U, k) tables travel by all-to-all; rank p merges user slice p.
+    Returns (ids, scores) for this rank's user slice, or for all users when ``gather``.
+    """
+    n_users_ranked = users.numel()
+    assert n_users_ranked % world_size == 0, "pad the user list to a multiple of world_size"
+    i0, i1 = item_shard(item_vecs.shape[0], world_size, rank)
+    part_ids, part_sc = rank_fn(mask_graph, user_vecs, item_vecs, k, users, (i0, i1))
+    per = n_users_ranked // world_size
+    recv_ids = torch.empty_like(part_ids)
+    recv_sc = torch.empty_like(part_sc)
+    if world_size > 1:
+        dist.all_to_all_single(recv_ids, part_ids.contiguous(), group=group)
+        dist.all_to_all_single(recv_sc, part_sc.contiguous(), group=group)
+    else:
+        recv_ids, recv_sc = part_ids, part_sc
+    my_users = users[rank * per:(rank + 1) * per].contiguous()
+    ids, sc = merge_fn(mask_graph, recv_ids.view(world_size, per, k), recv_sc.view(world_size, per, k), my_users)
+    if gather and world_size > 1:
+        all_ids = torch.empty((n_users_ranked, k), dtype=ids.dtype, device=ids.device)
+        all_sc = torch.empty((n_users_ranked, k), dtype=sc.dtype, device=sc.device)
+        dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
+        dist.all_gather_into_tensor(all_sc, sc.contiguous(), group=group)
+        return all_ids, all_sc
+    return ids, sc

@@ -179,6 +179,24 @@ def propagate_fwd(g: Graph, user_w: torch.Tensor, item_w: torch.Tensor, n_layers
     return out
 
 
+def propagate_host(g: Graph, h_user_w: torch.Tensor, h_item_w: torch.Tensor, h_out: torch.Tensor, n_layers: int,
+                   d_stage: torch.Tensor, single: bool = False) -> torch.Tensor:
+    """representation with HOST buffers (pinned): H2D of E0, L fused layers, D2H of the (N, d) result, all
+    enqueued on the current stream by one C-ABI call.  ``d_stage`` is a (2N, d) device staging buffer."""
+    for t, name in ((h_user_w, "h_user_w"), (h_item_w, "h_item_w"), (h_out, "h_out")):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.TgcnError(f"{name} must be a contiguous fp32 host tensor")
+    d = h_user_w.shape[1]
+    _chk(d_stage, torch.float32, "d_stage", 2)
+    if d_stage.numel() < 2 * g.n_nodes * d:
+        raise _lib.TgcnError("d_stage must hold 2·N·d floats")
+    ws = g.workspace(d, n_layers)
+    with torch.cuda.device(g.device):
+        check(g.lib.tgcn_propagate_host(g.handle, d, n_layers, int(single), h_user_w.data_ptr(), h_item_w.data_ptr(),
+                                        h_out.data_ptr(), _ptr(d_stage), _ptr(ws), ws.numel(), _stream()))
+    return h_out
+
+
 def propagate_bwd(g: Graph, grad_out: torch.Tensor, n_layers: int, single: bool = False,
                   keep: Optional[torch.Tensor] = None, dropout: float = 0.0,
                   grad_in: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:

@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--topk", type=int, default=20)
+    ap.add_argument("--mg-scheme", default="bipartite", choices=["bipartite", "rowblock"],
+                    help="multi-GPU propagation: users partitioned + item-table all-reduce, or row blocks + all-gather")
     return ap.parse_args()
 
 
@@ -254,7 +256,7 @@ def main():
         launches_per_step = L * (2 if graph.n_segments > 0 else 1)
         parallelism = "single GPU"
         scaling = "weak"
-    else:
+    elif args.mg_scheme == "rowblock":
         part = tdist.RowPartition(w["rowptr"], world)
         rp, col, val = part.local_block(rank, w["rowptr"], w["col"], w["val"])
         s, e = part.rows(rank)
@@ -271,9 +273,33 @@ def main():
         times = timed_steps(step, args.steps, args.warmup, flush, torch)
         dist.barrier()
         launches_per_step = L * (2 if lgraph.n_segments > 0 else 1)
-        parallelism = f"row-block x{world}, NCCL all-gather between hops"
+        parallelism = f"row-block x{world}, NCCL all-gather of layer embeddings between hops"
         scaling = "strong"
         extra["comm_bytes_per_hop_per_rank"] = prop.comm_bytes_per_hop
+        rows_local = e - s
+    else:
+        part = tdist.BipartitePartition(w["rowptr"], nu, ni, world)
+        u0, u1 = part.users(rank)
+        ugraph = ops.Graph(nu, ni, *part.user_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=u0, block=True)
+        ugraph.set_mask_col_offset(0)
+        igraph = ops.Graph(nu, ni, *part.item_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=nu, block=True)
+        prop = tdist.BipartitePropagator(part, rank, ugraph, igraph, d, L, dev)
+        e0_u = w["uw"][u0:u1].contiguous()
+        out_u = torch.empty((u1 - u0, d), dtype=torch.float32, device=dev)
+        out_i = torch.empty((ni, d), dtype=torch.float32, device=dev)
+
+        def step():
+            prop.propagate(e0_u, w["iw"], out_u, out_i)
+
+        dist.barrier()
+        sampler.start()
+        times = timed_steps(step, args.steps, args.warmup, flush, torch)
+        dist.barrier()
+        launches_per_step = 2 * L * (2 if (ugraph.n_segments + igraph.n_segments) > 0 else 1) + 1
+        parallelism = f"users partitioned x{world} by nnz, item table replicated: NCCL all-reduce of (I, d) per hop overlapped with the user-row SpMM"
+        scaling = "strong"
+        extra["comm_bytes_per_hop_per_rank"] = prop.comm_bytes_per_hop
+        rows_local = (u1 - u0) + ni
     torch.cuda.synchronize()
     total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -292,7 +318,7 @@ def main():
 
             def e2e_step():
                 ops.propagate_host(graph, h_u, h_i, h_o, L, stage)
-        else:
+        elif args.mg_scheme == "rowblock":
             h_e0 = torch.empty_like(e0, device="cpu").pin_memory().copy_(e0.cpu())
             h_o = torch.empty_like(out_local, device="cpu").pin_memory()
             d_e0 = torch.empty_like(e0)
@@ -301,17 +327,31 @@ def main():
                 d_e0.copy_(h_e0, non_blocking=True)
                 prop.propagate(d_e0, out_local)
                 h_o.copy_(out_local, non_blocking=True)
+        else:
+            h_u = torch.empty_like(e0_u, device="cpu").pin_memory().copy_(e0_u.cpu())
+            h_i = torch.empty_like(w["iw"], device="cpu").pin_memory().copy_(w["iw"].cpu())
+            h_ou = torch.empty_like(out_u, device="cpu").pin_memory()
+            h_oi = torch.empty_like(out_i, device="cpu").pin_memory()
+            d_u, d_i = torch.empty_like(e0_u), torch.empty_like(w["iw"])
+
+            def e2e_step():
+                d_u.copy_(h_u, non_blocking=True)
+                d_i.copy_(h_i, non_blocking=True)
+                prop.propagate(d_u, d_i, out_u, out_i)
+                h_ou.copy_(out_u, non_blocking=True)
+                h_oi.copy_(out_i, non_blocking=True)
         if world > 1:
             dist.barrier()
         et = timed_steps(e2e_step, max(3, args.steps // 2), 2, flush, torch)
         e_ms = torch.tensor([sum(et) / len(et)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-        rows_local = n if world == 1 else (e - s)
+        if world == 1:
+            rows_local = n
         e2e = {"value": nnz * L / (float(e_ms) * 1e-3), "unit": "edges/s", "ms_per_step": float(e_ms),
                "h2d_bytes_per_step": rows_local * d * 4, "d2h_bytes_per_step": rows_local * d * 4,
                "api": "tgcn_propagate_host (pinned host E0 -> device, L layers, result -> pinned host)" if world == 1
-               else "host-pinned E0 shard -> device, L hops with all-gather, result shard -> host"}
+               else "host-pinned E0 shard -> device, L hops with the collective, result shard -> pinned host"}
 
     # ---- eval leg: fused score + mask + top-k ----------------------------------------------------------------
     ev = None
@@ -334,17 +374,48 @@ def main():
                 h_ids.copy_(ids, non_blocking=True)
                 h_sc.copy_(sc, non_blocking=True)
         else:
-            full = prop.gather_full(out_local)
-            mask_rows = int(w["rowptr"][nu])
-            mgraph = ops.Graph(nu, ni, w["rowptr"][:nu + 1].contiguous(), w["col"][:mask_rows].contiguous(),
-                               w["val"][:mask_rows].contiguous(), row_begin=0, block=True)
+            # headline: user-range sharding (comm-free): every rank ranks a slice of ITS users against all items
             n_eval = args.eval_users or 16384 * world
             n_eval = (n_eval + world - 1) // world * world
-            users = torch.arange(n_eval, dtype=torch.int32, device=dev)
+            per = n_eval // world
+            if args.mg_scheme == "rowblock":
+                full = prop.gather_full(out_local)
+                u_tab, i_tab = full[:nu], full[nu:]
+                sample = torch.arange(rank * per, (rank + 1) * per, dtype=torch.int32, device=dev)
+                mrows = int(w["rowptr"][nu])
+                mgraph = ops.Graph(nu, ni, w["rowptr"][:nu + 1].contiguous(), w["col"][:mrows].contiguous(),
+                                   w["val"][:mrows].contiguous(), row_begin=0, block=True)
 
-            def eval_step():
-                return tdist.sharded_eval_topk(mgraph, full[:nu], full[nu:], users, k, rank, world)
+                def eval_step():
+                    return ops.eval_topk(mgraph, u_tab, i_tab, k, users=sample)
+            else:
+                per = min(per, u1 - u0)
+                n_eval = per * world
+                sample = torch.arange(u0, u0 + per, dtype=torch.int32, device=dev)
+                mrows = int(w["rowptr"][nu])
+                mgraph = ops.Graph(nu, ni, w["rowptr"][:nu + 1].contiguous(), w["col"][:mrows].contiguous(),
+                                   w["val"][:mrows].contiguous(), row_begin=0, block=True)
 
+                def eval_step():
+                    return ops.eval_topk(ugraph, out_u, out_i, k, users=sample, by_position=True)
+
+                # north_star variant: item-range sharding + cross-GPU merge over the same users
+                all_users = torch.empty(n_eval, dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(all_users, sample)
+                all_vecs = torch.empty((n_eval, d), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(all_vecs, out_u[:per].contiguous())
+
+                def eval_item_sharded():
+                    return tdist.sharded_eval_topk(mgraph, all_vecs, out_i, all_users, k, rank, world, by_position=True)
+
+                a_ids, a_sc = eval_step()
+                b_ids, b_sc = eval_item_sharded()
+                extra["item_sharded_matches_user_sharded"] = bool(torch.equal(a_ids, b_ids) and torch.equal(a_sc, b_sc))
+                t_is = timed_steps(eval_item_sharded, args.eval_steps, 1, flush, torch)
+                is_ms = torch.tensor([sum(t_is) / len(t_is)], dtype=torch.float64, device=dev)
+                dist.all_reduce(is_ms, op=dist.ReduceOp.MAX)
+                extra["eval_item_sharded"] = {"users_per_s": n_eval / (float(is_ms) * 1e-3), "ms": float(is_ms),
+                                              "sharding": f"item range x{world}, all-to-all of partial top-k + merge"}
             eval_e2e = None
         t_ev = timed_steps(eval_step, args.eval_steps, 1, flush, torch)
         ev_ms = torch.tensor([sum(t_ev) / len(t_ev)], dtype=torch.float64, device=dev)
@@ -353,7 +424,7 @@ def main():
         ev = {"users_per_s": n_eval / (float(ev_ms) * 1e-3), "k": k, "n_users_ranked": n_eval, "n_items": ni,
               "ms": float(ev_ms), "score_flops_per_s": 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
               "kernel": "eval_topk_simt_kernel (exact fp32 FMA) + topk_merge_kernel",
-              "sharding": "single GPU" if world == 1 else f"item range x{world}, all-to-all + merge"}
+              "sharding": "single GPU" if world == 1 else f"user range x{world} (comm-free); item-range variant in eval_item_sharded"}
         if eval_e2e is not None:
             t_e = timed_steps(eval_e2e, args.eval_steps, 1, flush, torch)
             ev["e2e_users_per_s"] = n_eval / (sum(t_e) / len(t_e) * 1e-3)

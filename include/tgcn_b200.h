@@ -57,6 +57,9 @@ int tgcn_graph_create_block(tgcn_graph_t** out, int64_t n_users, int64_t n_items
 int tgcn_graph_build_transpose_perm(tgcn_graph_t* g, tgcn_stream_t stream);
 void tgcn_graph_destroy(tgcn_graph_t* g);
 int64_t tgcn_graph_num_segments(const tgcn_graph_t* g);
+/* Eval masks read the user rows of a handle: local row = user id - row_begin, an entry equals col_offset + item id.
+ * col_offset defaults to n_users (global column numbering); a row block whose columns are item ids sets 0. */
+int tgcn_graph_set_mask_col_offset(tgcn_graph_t* g, int64_t col_offset);
 /* bytes of caller-provided workspace for propagate_fwd / propagate_bwd */
 int64_t tgcn_propagate_workspace_bytes(const tgcn_graph_t* g, int64_t d, int32_t n_layers);
 
@@ -74,6 +77,11 @@ int tgcn_spmm_ex(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const 
                  const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
                  const float* const* h_add_user, const float* const* h_add_item, float divisor,
                  int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* a5 alone: out = (add_0 + ... + add_{n_add-1}) / divisor over n floats (n % 4 == 0) — layer_combination
+ * (base_model.py:150-157) for a table that no local SpMM produces (the all-reduced item table in multi-GPU runs). */
+int tgcn_layer_mean(int64_t n, int32_t n_add, const float* const* h_add, float divisor, float* d_out,
+                    tgcn_stream_t stream);
 
 /* a2+a3+a4×L+a5  BaseModel.representation (base_model.py:88-106, :150-164).
  * E0 is read through two base pointers (no torch.cat); d_keep is the Bernoulli keep-mask over the

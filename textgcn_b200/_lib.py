@@ -26,10 +26,12 @@ SIGNATURES = {
     "tgcn_graph_build_transpose_perm": (c_int32, [_P, _P]),
     "tgcn_graph_destroy": (None, [_P]),
     "tgcn_graph_num_segments": (c_int64, [_P]),
+    "tgcn_graph_set_mask_col_offset": (c_int32, [_P, c_int64]),
     "tgcn_propagate_workspace_bytes": (c_int64, [_P, c_int64, c_int32]),
     "tgcn_spmm_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, _P]),
     "tgcn_spmm_ex": (c_int32, [_P, c_int64, _P, _P, _P, c_float, c_int32, c_int32, POINTER(c_void_p), POINTER(c_void_p),
                                c_float, c_int32, _P, _P, c_int64, _P]),
+    "tgcn_layer_mean": (c_int32, [c_int64, c_int32, POINTER(c_void_p), c_float, _P, _P]),
     "tgcn_propagate_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, c_int64, _P]),
     "tgcn_propagate_bwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, c_float, c_int32, _P, _P, c_int64, _P]),
     "tgcn_propagate_host": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, c_int64, _P]),

@@ -246,7 +246,7 @@ int tgcn_adv_select(const tgcn_graph_t* mask_graph, int64_t d, int64_t batch, in
                     const int32_t* d_cands, const float* d_emb, int32_t kmax, int32_t* d_out_negs, int32_t* d_out_counts,
                     float* d_out_scores, tgcn_stream_t stream) {
   TGCN_REQUIRE(mask_graph != nullptr, "graph is NULL");
-  TGCN_REQUIRE(mask_graph->row_begin == 0 && mask_graph->n_rows >= mask_graph->n_users, "graph must cover all user rows");
+  TGCN_REQUIRE(mask_graph->row_begin == 0 && mask_graph->n_rows >= mask_graph->n_users && !mask_graph->is_block, "adv_select needs a whole-graph handle");
   TGCN_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 * kMaxChunks, "embedding width d=%lld must be a multiple of 4 and <= %d", (long long)d, 128 * kMaxChunks);
   TGCN_REQUIRE(batch > 0 && n_cand > 0 && n_cand <= TGCN_ADV_MAX_CANDIDATES, "bad sizes: batch=%lld n_cand=%d (max %d)", (long long)batch, n_cand, TGCN_ADV_MAX_CANDIDATES);
   TGCN_REQUIRE(kmax > 0, "kmax must be positive");

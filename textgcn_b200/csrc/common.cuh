@@ -29,8 +29,8 @@ void set_error(const char* fmt, ...);
 
 #define TGCN_CHECK_LAUNCH() TGCN_CHECK_CUDA(cudaGetLastError())
 
-constexpr int kSplitThreshold = 512;  // rows longer than this are cut into segments
-constexpr int kSegmentLen = 256;      // nnz per segment of a long row
+constexpr int kSplitThreshold = 128;  // rows longer than this are cut into segments
+constexpr int kSegmentLen = 64;       // nnz per segment of a long row
 
 struct Segment {  // one warp's share of a long row
   int row;        // local row index
@@ -62,6 +62,8 @@ struct tgcn_graph {
   tgcn::SplitRow* split_rows;
   int n_split_rows;
   int max_degree;
+  int mask_col_off;  // eval masks: entry value = mask_col_off + item id (n_users unless overridden)
+  int bipartite;  // verified at creation: user rows reference only item columns and vice versa
 };
 
 namespace tgcn {

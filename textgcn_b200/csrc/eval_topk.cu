@@ -333,11 +333,11 @@ static void split_plan(int64_t n_rank, int64_t n_items_range, int* n_splits, int
 
 static int mask_fields(const tgcn_graph* g, const int** rowptr, const int** col, int* row_begin, int* col_off) {
   if (g) {
-    TGCN_REQUIRE(g->row_begin == 0 && g->n_rows >= g->n_users, "mask graph must cover all user rows");
+    // rows of the handle are users row_begin .. row_begin + n_rows - 1 (the caller only ranks users it covers)
     *rowptr = g->rowptr;
     *col = g->col;
-    *row_begin = 0;
-    *col_off = (int)g->n_users;
+    *row_begin = (int)g->row_begin;
+    *col_off = g->mask_col_off;
   } else {
     *rowptr = nullptr;
     *col = nullptr;

@@ -45,6 +45,40 @@ __global__ void transpose_perm_kernel(const int* __restrict__ rowptr, const int*
   }
 }
 
+// Per row: columns strictly increasing (the binary searches rely on it) and, for a whole graph, on the other
+// side of the user/item boundary.  flags[0] |= unsorted, flags[1] |= not bipartite.
+__global__ void check_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_rows, int n_users,
+                                  int* __restrict__ flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+  bool unsorted = false;
+  for (int p = b + 1; p < e; ++p) unsorted |= __ldg(col + p) <= __ldg(col + p - 1);
+  if (unsorted) flags[0] = 1;
+  if (e > b) {
+    const bool bad = r < n_users ? __ldg(col + b) < n_users : __ldg(col + e - 1) >= n_users;
+    if (bad) flags[1] = 1;
+  }
+}
+
+static int check_rows(tgcn_graph* g, cudaStream_t stream) {
+  int* flags = nullptr;
+  int h[2] = {0, 0};
+  TGCN_CHECK_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(flags, 0, 2 * sizeof(int), stream);
+  if (e == cudaSuccess) {
+    check_rows_kernel<<<(unsigned)((g->n_rows + 255) / 256), 256, 0, stream>>>(g->rowptr, g->col, (int)g->n_rows, (int)g->n_users, flags);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(flags);
+  TGCN_REQUIRE(e == cudaSuccess, "check_rows_kernel failed: %s", cudaGetErrorString(e));
+  TGCN_REQUIRE(h[0] == 0, "CSR columns must be strictly increasing within every row (coalesced, sorted COO order)");
+  g->bipartite = g->is_block ? 0 : (h[1] == 0);
+  return 0;
+}
+
 static int build_segments(tgcn_graph* g, cudaStream_t stream) {
   std::vector<int> rowptr(g->n_rows + 1);
   TGCN_CHECK_CUDA(cudaMemcpyAsync(rowptr.data(), g->rowptr, sizeof(int) * (g->n_rows + 1), cudaMemcpyDeviceToHost, stream));
@@ -116,7 +150,10 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->segments = nullptr;
   g->split_rows = nullptr;
   g->n_segments = g->n_split_rows = 0;
+  g->bipartite = 0;
+  g->mask_col_off = (int)n_users;
   int rc = build_segments(g, (cudaStream_t)stream);
+  if (rc == 0 && nnz > 0) rc = check_rows(g, (cudaStream_t)stream);
   if (rc != 0) {
     tgcn_graph_destroy(g);
     return rc;
@@ -174,5 +211,12 @@ void tgcn_graph_destroy(tgcn_graph_t* g) {
 }
 
 int64_t tgcn_graph_num_segments(const tgcn_graph_t* g) { return g ? g->n_segments : -1; }
+
+int tgcn_graph_set_mask_col_offset(tgcn_graph_t* g, int64_t col_offset) {
+  TGCN_REQUIRE(g != nullptr, "graph is NULL");
+  TGCN_REQUIRE(col_offset >= 0 && col_offset < (1ll << 31), "bad column offset");
+  g->mask_col_off = (int)col_offset;
+  return 0;
+}
 
 }  // extern "C"

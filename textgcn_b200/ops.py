@@ -115,6 +115,9 @@ class Graph:
             self._ws["buf"] = ws
         return ws
 
+    def set_mask_col_offset(self, off: int) -> None:
+        check(self.lib.tgcn_graph_set_mask_col_offset(self.handle, int(off)))
+
     def build_transpose_perm(self) -> None:
         with torch.cuda.device(self.device):
             check(self.lib.tgcn_graph_build_transpose_perm(self.handle, _stream()))
@@ -148,6 +151,17 @@ def spmm_ex(g: Graph, x: torch.Tensor, y: torch.Tensor, addends: Sequence[torch.
         check(g.lib.tgcn_spmm_ex(g.handle, d, _ptr(x), None, _ptr(keep), float(dropout), int(transposed), n, arr, nul,
                                  float(divisor), int(accumulate), _ptr(y), _ptr(ws), ws.numel(), _stream()))
     return y
+
+
+def layer_mean(addends: Sequence[torch.Tensor], out: torch.Tensor, divisor: Optional[float] = None) -> torch.Tensor:
+    """out = (Σ addends) / divisor (default: their count) — layer_combination for a table no local SpMM produces."""
+    lib = _lib.load()
+    n = len(addends)
+    arr = (ctypes.c_void_p * n)(*[_chk(a, torch.float32, "addend").data_ptr() for a in addends])
+    _chk(out, torch.float32, "out")
+    with torch.cuda.device(out.device):
+        check(lib.tgcn_layer_mean(out.numel(), n, arr, float(n if divisor is None else divisor), _ptr(out), _stream()))
+    return out
 
 
 def _keep_u8(keep: torch.Tensor) -> torch.Tensor:

@@ -8,10 +8,12 @@ A "step" is one pass of the hot path over the whole graph: ``representation`` = 
 ``value`` = nnz(Â)·L / t with inputs resident in HBM; ``e2e`` = the same through the host-buffer C-ABI call
 (``tgcn_propagate_host``: H2D of E0, L layers, D2H of the result).  Workloads (``config.workload``):
   N = 1 : "c2" — BASELINE.json configs[1], Electronics-shaped (190k users, 63k items, 1.7M edges, d 64, 3 layers)
-  N > 1 : "c5" — configs[4] (10M users, 2M items, 200M edges, d 128, 4 layers), STRONG scaling: Â row-partitioned
-          by nnz, NCCL all-gather of layer embeddings between hops, item-sharded eval with cross-GPU top-k merge.
+  N > 1 : "c5" — configs[4] (10M users, 2M items, 200M edges, d 128, 4 layers), STRONG scaling.  Default scheme:
+          users partitioned by nnz, item table replicated and all-reduced (NCCL) once per hop, overlapped with the
+          user-row SpMM; `--mg-scheme rowblock` = row blocks of Â + all-gather of layer embeddings between hops.
+          Eval: user-range sharding (comm-free) and the item-range variant with a cross-GPU top-k merge.
 Between timed iterations L2 is flushed (a 256 MiB write); timing is CUDA events on the launching stream, max over
-ranks.  The JSON line also carries ``roofline`` (dominant kernel: spmm_rows_kernel, HBM bound), ``cpu_baseline``
+ranks.  The JSON line also carries ``roofline`` (dominant kernel: spmm_group_kernel, HBM bound), ``cpu_baseline``
 (oracle port on the host cores, N = 1 only), ``eval`` (users/s) and ``clocks``.
 """
 from __future__ import annotations
@@ -423,8 +425,17 @@ def main():
             dist.all_reduce(ev_ms, op=dist.ReduceOp.MAX)
         ev = {"users_per_s": n_eval / (float(ev_ms) * 1e-3), "k": k, "n_users_ranked": n_eval, "n_items": ni,
               "ms": float(ev_ms), "score_flops_per_s": 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
-              "kernel": "eval_topk_simt_kernel (exact fp32 FMA) + topk_merge_kernel",
+              "kernel": "tf32_split_kernel x2 + eval_topk_tc_kernel (3xTF32 tcgen05.mma, TMEM accumulators, TMA operands) + "
+                        "topk_merge_kernel",
+              "tensor_flops_per_s": 3 * 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
               "sharding": "single GPU" if world == 1 else f"user range x{world} (comm-free); item-range variant in eval_item_sharded"}
+        if world == 1:
+            n_f = min(n_eval, 32768)
+            users_f = users[:n_f].contiguous()
+            t_f = timed_steps(lambda: ops.eval_topk(graph, emb[:nu], emb[nu:], k, users=users_f, precision="fp32"),
+                              max(1, args.eval_steps - 1), 1, flush, torch)
+            ev["fp32_simt_users_per_s"] = n_f / (sum(t_f) / len(t_f) * 1e-3)
+            ev["fp32_simt_note"] = f"eval_topk_simt_kernel (exact fp32 FMA) on {n_f} users"
         if eval_e2e is not None:
             t_e = timed_steps(eval_e2e, args.eval_steps, 1, flush, torch)
             ev["e2e_users_per_s"] = n_eval / (sum(t_e) / len(t_e) * 1e-3)
@@ -463,7 +474,7 @@ def main():
                        "interactions_per_s": value / 2},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "kernel": "spmm_rows_kernel", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "spmm_group_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_step": step_bytes, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "per_gpu": world > 1},
             "eval": ev, "clocks": sampler.summary(),

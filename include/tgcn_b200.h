@@ -129,12 +129,15 @@ int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch,
  * Items the user interacted with in `mask_graph` (user rows of Â = train_user_dict) are excluded;
  * when fewer than k unmasked items exist the list is completed with masked items, lowest id first,
  * score -inf.  Order is the canonical strict order (score desc, item id asc).
+ * precision: 1 = exact fp32 FMA (SIMT kernel); 2 = 3xTF32 on the tcgen05 tensor cores (K % 32 == 0, K <= 128, no bias;
+ * scores within ~1e-6 norm-wise of fp32, bit-exact for TF32-representable inputs); 0 = 3xTF32 when eligible, else fp32.
  * Outputs (n_rank, k) int32 ids and fp32 scores.  k <= TGCN_MAX_TOPK. */
-int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int32_t k);
+int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
 int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users,
                    const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K,
                    int64_t item_begin, int64_t item_end, const float* d_user_bias, const float* d_item_bias,
-                   int32_t vecs_by_position, int32_t k, int32_t finalize, int32_t* d_out_ids, float* d_out_scores,
+                   int32_t vecs_by_position, int32_t precision, int32_t k, int32_t finalize, int32_t* d_out_ids,
+                   float* d_out_scores,
                    void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
 
 /* Cross-shard / cross-GPU merge of n_parts partial top-k tables (n_parts, n_rows, k) under the same

@@ -38,12 +38,12 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_size_queries_and_argument_validation_without_gpu(lib):
     assert lib.tgcn_bpr_workspace_bytes(2048) >= 2048 * 8
-    assert lib.tgcn_eval_workspace_bytes(2048, 63000, 20) > 0
-    assert lib.tgcn_eval_workspace_bytes(0, 63000, 20) < 0
+    assert lib.tgcn_eval_workspace_bytes(2048, 63000, 64, 20) > 0
+    assert lib.tgcn_eval_workspace_bytes(0, 63000, 64, 20) < 0
     # argument errors are reported through the return code + tgcn_last_error, never by aborting
     rc = lib.tgcn_topk_merge(None, 0, None, 1, 20, None, None, 1, None, None, None)
     assert rc != 0 and b"bad sizes" in lib.tgcn_last_error()
-    rc = lib.tgcn_eval_topk(None, 8, None, None, 64, None, 64, 63, 0, 10, None, None, 0, 20, 1, None, None, None, 0, None)
+    rc = lib.tgcn_eval_topk(None, 8, None, None, 64, None, 64, 63, 0, 10, None, None, 0, 0, 20, 1, None, None, None, 0, None)
     assert rc != 0 and b"bad shapes" in lib.tgcn_last_error()
     handle = ctypes.c_void_p()
     rc = lib.tgcn_graph_create(ctypes.byref(handle), 5, 4, 26, None, None, None, None)

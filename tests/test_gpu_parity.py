@@ -165,8 +165,10 @@ def test_predict_topk_matches_reference_golden(ops, case):
             assert np.allclose(res[m], g["metric_" + m], rtol=0, atol=1e-12), m
 
 
-@pytest.mark.parametrize("n_rank,n_items,d,k", [(300, 5000, 64, 20), (40, 20000, 128, 40), (1000, 700, 32, 128), (5, 130, 64, 7)])
-def test_topk_bit_exact_on_exact_arithmetic(ops, n_rank, n_items, d, k):
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("n_rank,n_items,d,k", [(300, 5000, 64, 20), (40, 20000, 128, 40), (1000, 700, 32, 64), (5, 130, 64, 7),
+                                                (130, 1000, 96, 20)])
+def test_topk_bit_exact_on_exact_arithmetic(ops, n_rank, n_items, d, k, precision):
     """Dyadic-grid embeddings make every dot product exact in fp32 in any summation order, so the lists must be
     bit-identical to the canonical order, ties (plentiful here) included (SURVEY.md §8c iv)."""
     rng = np.random.default_rng(n_items)
@@ -177,18 +179,39 @@ def test_topk_bit_exact_on_exact_arithmetic(ops, n_rank, n_items, d, k):
     row, col, val = O.norm_adj_coo(tu, ti, nu, n_items)
     gr = ops.Graph.from_norm_matrix(O.sparse_tensor(row, col, val, nu + n_items).to(DEV), nu, n_items)
     users = rng.permutation(nu)[:n_rank]
-    ids, sc = ops.eval_topk(gr, _cuda(ue), _cuda(ie), k, users=ops.as_index(users, DEV))
+    ids, sc = ops.eval_topk(gr, _cuda(ue), _cuda(ie), k, users=ops.as_index(users, DEV), precision=precision)
     tl = O.train_lists_from_edges(tu, ti, nu)
     o_ids, o_sc = O.predict_topk(torch.from_numpy(ue), torch.from_numpy(ie), users, tl, k, round_decimals=None)
     assert np.array_equal(ids.cpu().numpy(), o_ids)
     assert np.array_equal(sc.cpu().numpy(), o_sc)
     # item-sharded evaluation + merge gives the same table (multi-GPU eval path)
     cuts = [0, n_items // 3, n_items // 2, n_items]
-    parts = [ops.eval_topk(gr, _cuda(ue), _cuda(ie), k, users=ops.as_index(users, DEV), item_range=(a, b), finalize=False)
+    parts = [ops.eval_topk(gr, _cuda(ue), _cuda(ie), k, users=ops.as_index(users, DEV), item_range=(a, b), finalize=False,
+                           precision=precision)
              for a, b in zip(cuts[:-1], cuts[1:])]
     m_ids, m_sc = ops.topk_merge(gr, torch.stack([p[0] for p in parts]).contiguous(),
                                  torch.stack([p[1] for p in parts]).contiguous(), users=ops.as_index(users, DEV))
     assert np.array_equal(m_ids.cpu().numpy(), o_ids) and np.array_equal(m_sc.cpu().numpy(), o_sc)
+
+
+@pytest.mark.parametrize("d,n_items,k", [(64, 9000, 20), (128, 3000, 40), (32, 1500, 20)])
+def test_3xtf32_scores_within_stated_tolerance(ops, d, n_items, k):
+    """The tensor-core path (3xTF32) against fp64: |Δscore| <= 1e-5·‖u‖‖i‖, ids tie-aware."""
+    gen = torch.Generator().manual_seed(d)
+    nu = 700
+    ue = torch.randn(nu, d, generator=gen) * 0.3
+    ie = torch.randn(n_items, d, generator=gen) * 0.3
+    ids, sc = ops.eval_topk(None, ue.to(DEV), ie.to(DEV), k, precision="3xtf32")
+    ids32, sc32 = ops.eval_topk(None, ue.to(DEV), ie.to(DEV), k, precision="fp32")
+    ref = (ue.double() @ ie.double().T).numpy()
+    o_ids, o_sc = O.canonical_topk(ref, k)
+    bound = 1e-5 * float(ue.norm(dim=1).max() * ie.norm(dim=1).max())
+    assert np.abs(sc.cpu().numpy() - o_sc).max() <= bound
+    assert np.abs(sc32.cpu().numpy() - o_sc).max() <= bound
+    for got_ids, got_sc in ((ids, sc), (ids32, sc32)):
+        st = O.topk_lists_equivalent(got_ids.cpu().numpy().astype(np.int64), got_sc.cpu().numpy(), o_ids, o_sc.astype(np.float32),
+                                     rtol=0, atol=2 * bound)
+        assert st["bad"] == 0 and st["exact"] >= st["rows"] - 5, st
 
 
 def test_topk_short_lists_are_completed_with_masked_items(ops):

@@ -38,9 +38,9 @@ SIGNATURES = {
     "tgcn_bpr_workspace_bytes": (c_int64, [c_int64]),
     "tgcn_bpr_fwd_bwd": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float,
                                    _P, _P, _P, _P, c_int64, _P]),
-    "tgcn_eval_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32]),
+    "tgcn_eval_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
     "tgcn_eval_topk": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
-                                 c_int32, c_int32, c_int32, _P, _P, _P, c_int64, _P]),
+                                 c_int32, c_int32, c_int32, c_int32, _P, _P, _P, c_int64, _P]),
     "tgcn_topk_merge": (c_int32, [_P, c_int64, _P, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P]),
     "tgcn_adv_select": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P, _P]),
     "tgcn_ltr_pairwise_features": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P,

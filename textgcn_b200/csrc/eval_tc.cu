@@ -1,0 +1,462 @@
+// Full-ranking evaluation on the 5th-generation tensor cores: the user×item score GEMM runs as 3xTF32
+// tcgen05.mma (hi·hi + lo·hi + hi·lo, fp32 accumulation in TMEM) fused with train-item masking and a streaming
+// per-user top-k, so the score matrix exists only in tensor memory (base_model.py:255-261).
+//
+//   * Operands are pre-split once per call into [hi | lo] TF32 halves (hi = rna_tf32(x), lo = rna_tf32(x - hi);
+//     both have zero low mantissa bits, so the tensor core's input truncation is exact).  Dropping lo·lo bounds
+//     the relative product error by ~2^-21; scores agree with the fp32 SGEMM to ~1e-6 norm-wise (the parity
+//     budget is 1e-5), and are bit-exact whenever the inputs are TF32-representable (the tie fixture).
+//   * One CTA = 128 users × the whole item range (or one split of it).  The user tile (128 × 2K fp32) is loaded
+//     ONCE by TMA and stays resident in shared memory; item tiles of BN rows stream through an mbarrier ring of
+//     128-byte-swizzled K-chunks (32 fp32 = one swizzle row).  Warp 0 = TMA producer, warp 1 = MMA issuer
+//     (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue.
+//   * Accumulators: 2 × BN TMEM columns (double buffered): the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * Epilogue: TMEM lane = user row, so each of the 128 epilogue threads owns one user: it reads its row with
+//     tcgen05.ld (32 columns per instruction), compares every score against its k-th best (one FSETP per score)
+//     and only on a hit checks the train mask (binary search in the user row of Â) and inserts into its private
+//     sorted list in shared memory.  Items arrive in increasing id order, so a strict '>' keeps the canonical
+//     (score desc, id asc) order.
+//
+// Roofline: tensor pipe, 3 × 2·K TF32 flops per score (MMA floor 128 cycles per 128×256×8 instruction).
+#include <cuda.h>
+#include <limits.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tgcn {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+constexpr int TC_CHUNK = 32;            // fp32 per 128-byte swizzle row
+constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
+constexpr int TC_MAX_STAGES = 8;
+
+struct TcArgs {
+  int n_rank, K, n_range, item_begin, k;
+  int tiles_per_split, n_stages;
+  const int* users;
+  const int* mrowptr;
+  const int* mcol;
+  int mrow_begin, mcol_off;
+  int* part_ids;
+  float* part_scores;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU (traps after ~2 s instead).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: 8-row atoms of 1024 B, SBO = 1024 B, LBO unused, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Thread-private insert into a descending list stored with stride 128 (one column of a [k][128] array).
+__device__ __noinline__ float thread_list_insert(float* ls, int* li, int k, float s, int id) {
+  int j = k - 1;
+  while (j > 0) {
+    const float ps = ls[(j - 1) * TC_BM];
+    const int pi = li[(j - 1) * TC_BM];
+    if (!ranks_before(s, id, ps, pi)) break;
+    ls[j * TC_BM] = ps;
+    li[j * TC_BM] = pi;
+    --j;
+  }
+  ls[j * TC_BM] = s;
+  li[j * TC_BM] = id;
+  return ls[(k - 1) * TC_BM];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const int KC = a.K / TC_CHUNK;
+  const int n_a = 2 * KC;
+  constexpr int B_STAGE_BYTES = BN * 128;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
+  uint8_t* gen_lists = gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES;
+  float* list_s = reinterpret_cast<float*>(gen_lists);        // [k][128]
+  int* list_i = reinterpret_cast<int*>(list_s + a.k * TC_BM);  // [k][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(list_i + a.k * TC_BM);
+  const uint32_t bar_a_full = smem_u32(bars + 0);
+  const uint32_t bar_b_full = smem_u32(bars + 1);                      // [TC_MAX_STAGES]
+  const uint32_t bar_b_empty = smem_u32(bars + 1 + TC_MAX_STAGES);     // [TC_MAX_STAGES]
+  const uint32_t bar_t_full = smem_u32(bars + 1 + 2 * TC_MAX_STAGES);  // [2]
+  const uint32_t bar_t_empty = smem_u32(bars + 3 + 2 * TC_MAX_STAGES); // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_MAX_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int n_tiles = (a.n_range + BN - 1) / BN;
+  const int tile_begin = blockIdx.y * a.tiles_per_split;
+  const int tile_end = min(n_tiles, tile_begin + a.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_i) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
+      mbar_init(bar_b_full + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_t_full + 8 * s, 1);
+      mbar_init(bar_t_empty + 8 * s, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 4) {
+    const int t = threadIdx.x - 128;
+    for (int j = 0; j < a.k; ++j) {
+      list_s[j * TC_BM + t] = -INFINITY;
+      list_i[j * TC_BM + t] = INT_MAX;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: resident user tile, then the item chunks of every tile ----
+      mbar_expect_tx(bar_a_full, n_a * TC_A_CHUNK_BYTES);
+      for (int c = 0; c < n_a; ++c) tma_load_2d(sA + c * TC_A_CHUNK_BYTES, &map_u, bar_a_full, c * TC_CHUNK, m0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int row0 = tile * BN;
+        for (int c = 0; c < n_a; ++c) {  // order: hi_0, lo_0, hi_1, lo_1, ...
+          const int colk = (c & 1) ? a.K + (c >> 1) * TC_CHUNK : (c >> 1) * TC_CHUNK;
+          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE_BYTES);
+          tma_load_2d(sB + stage * B_STAGE_BYTES, &map_i, bar_b_full + 8 * stage, colk, row0);
+          if (++stage == a.n_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer: D[128 x BN] (+)= A[128 x 8] · B[BN x 8]ᵀ, kind::tf32, fp32 accumulate in TMEM ----
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      mbar_wait(bar_a_full, 0);
+      tc_fence_after();
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(bar_t_empty + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < n_a; ++c) {
+          mbar_wait(bar_b_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t bb = sB + stage * B_STAGE_BYTES;
+          const int kc = c >> 1;
+          const uint32_t a_hi = sA + kc * TC_A_CHUNK_BYTES, a_lo = sA + (KC + kc) * TC_A_CHUNK_BYTES;
+          if ((c & 1) == 0) {  // B = hi chunk: hi·hi and lo·hi
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), idesc, accumulate);
+              accumulate = 1;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(bb + kk * 32), idesc, 1);
+          } else {  // B = lo chunk: hi·lo
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), idesc, 1);
+          }
+          umma_commit(bar_b_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == a.n_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(bar_t_full + 8 * as);  // accumulator of this tile complete
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: one thread per user row ----
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int t = ew * 32 + lane;
+    const int m = m0 + t;
+    const bool valid = m < a.n_rank;
+    const int user = valid ? (a.users ? __ldg(a.users + m) : m) : 0;
+    int mlo = 0, mhi = 0;
+    if (valid && a.mrowptr) {
+      mlo = __ldg(a.mrowptr + user - a.mrow_begin);
+      mhi = __ldg(a.mrowptr + user - a.mrow_begin + 1);
+    }
+    float* ls = list_s + t;
+    int* li = list_i + t;
+    float thr = -INFINITY;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(bar_t_full + 8 * as, aphase);
+      tc_fence_after();
+      const int n0 = tile * BN;
+#pragma unroll 1
+      for (int g = 0; g < BN / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + g * 32, v);
+        if (valid) {
+          const int nbase = n0 + g * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(v[j]);
+            if (s > thr && nbase + j < a.n_range) {
+              const int item = a.item_begin + nbase + j;
+              if (!sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) thr = thread_list_insert(ls, li, a.k, s, item);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_t_empty + 8 * as);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (valid) {
+      const size_t o = ((size_t)blockIdx.y * a.n_rank + m) * a.k;
+      for (int j = 0; j < a.k; ++j) {
+        a.part_ids[o + j] = li[j * TC_BM];
+        a.part_scores[o + j] = ls[j * TC_BM];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// out row r = [hi(x) | lo(x)] of source row (rows ? rows[r] : row_begin + r); K floats each half.
+__global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict__ src, int64_t ld, const int* __restrict__ rows,
+                                                         int64_t row_begin, int64_t n_rows, int K, float* __restrict__ out) {
+  const int k4 = K >> 2;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_rows * k4) return;
+  const int64_t r = t / k4;
+  const int c = (int)(t % k4) * 4;
+  const int64_t sr = rows ? (int64_t)__ldg(rows + r) : row_begin + r;
+  const float4 x = ldg4(src + sr * ld + c);
+  float xs[4] = {x.x, x.y, x.z, x.w}, hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(xs[i]));
+    hi[i] = __uint_as_float(h);
+    const float rem = xs[i] - hi[i];
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
+    lo[i] = __uint_as_float(l);
+  }
+  *reinterpret_cast<float4*>(out + r * 2 * K + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(out + r * 2 * K + K + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  TGCN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_CHUNK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TGCN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return 0;
+}
+
+static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
+
+// Shared-memory plan for the tensor-core kernel; returns 0 stages when it does not fit (caller falls back).
+static void tc_plan(int K, int k, int* bn, int* n_stages, size_t* smem) {
+  *bn = K <= 64 ? 256 : 128;
+  const size_t a_bytes = (size_t)(2 * (K / TC_CHUNK)) * TC_A_CHUNK_BYTES;
+  const size_t lists = (size_t)k * TC_BM * 8;
+  const size_t fixed = 1024 /*align slack*/ + a_bytes + lists + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
+  const size_t budget = 227 * 1024;
+  const size_t stage = (size_t)*bn * 128;
+  int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
+  if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
+  *n_stages = s;
+  *smem = fixed + (size_t)s * stage;
+}
+
+bool eval_tc_eligible(int64_t K, int32_t k) {
+  if (K % TC_CHUNK != 0 || K > 128 || K <= 0) return false;
+  int bn, st;
+  size_t sm;
+  tc_plan((int)K, k, &bn, &st, &sm);
+  return st >= 2;
+}
+
+int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, int n_splits) {
+  return al256(n_rank * 2 * K * 4) + al256(n_range * 2 * K * 4) + al256((int64_t)n_splits * n_rank * k * 4) * 2 + 256;
+}
+
+void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_splits, int* tiles_per_split);
+
+int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
+                 int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
+                 int64_t item_end, int32_t k, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
+                 float** part_scores_out, cudaStream_t s) {
+  int bn, n_stages;
+  size_t smem;
+  tc_plan((int)K, k, &bn, &n_stages, &smem);
+  TGCN_REQUIRE(n_stages >= 2, "3xTF32 path does not fit in shared memory for K=%lld k=%d", (long long)K, k);
+  const int64_t n_range = item_end - item_begin;
+  int n_splits, tps;
+  eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  const int64_t need = eval_tc_workspace_bytes(n_rank, n_range, K, k, n_splits);
+  TGCN_REQUIRE(d_workspace && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
+  char* ws = (char*)d_workspace;
+  float* u2 = (float*)ws;
+  float* i2 = (float*)(ws + al256(n_rank * 2 * K * 4));
+  int* part_ids = (int*)((char*)i2 + al256(n_range * 2 * K * 4));
+  float* part_scores = (float*)((char*)part_ids + al256((int64_t)n_splits * n_rank * k * 4));
+  const int k4 = (int)K / 4;
+  tf32_split_kernel<<<(unsigned)((n_rank * k4 + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, by_pos ? nullptr : d_users, 0, n_rank, (int)K, u2);
+  TGCN_CHECK_LAUNCH();
+  tf32_split_kernel<<<(unsigned)((n_range * k4 + 255) / 256), 256, 0, s>>>(d_item_vecs, ldi, nullptr, item_begin, n_range, (int)K, i2);
+  TGCN_CHECK_LAUNCH();
+  CUtensorMap map_u, map_i;
+  if (int rc = make_map(&map_u, u2, n_rank, 2 * K, TC_BM)) return rc;
+  if (int rc = make_map(&map_i, i2, n_range, 2 * K, bn)) return rc;
+  TcArgs a;
+  a.n_rank = (int)n_rank;
+  a.K = (int)K;
+  a.n_range = (int)n_range;
+  a.item_begin = (int)item_begin;
+  a.k = k;
+  a.tiles_per_split = tps;
+  a.n_stages = n_stages;
+  a.users = d_users;
+  a.mrowptr = mrowptr;
+  a.mcol = mcol;
+  a.mrow_begin = mrow_begin;
+  a.mcol_off = mcol_off;
+  a.part_ids = part_ids;
+  a.part_scores = part_scores;
+  dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
+  if (bn == 256) {
+    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    eval_topk_tc_kernel<256><<<grid, TC_THREADS, smem, s>>>(map_u, map_i, a);
+  } else {
+    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    eval_topk_tc_kernel<128><<<grid, TC_THREADS, smem, s>>>(map_u, map_i, a);
+  }
+  TGCN_CHECK_LAUNCH();
+  *n_splits_out = n_splits;
+  *part_ids_out = part_ids;
+  *part_scores_out = part_scores;
+  return 0;
+}
+
+}  // namespace tgcn

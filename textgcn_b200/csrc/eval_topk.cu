@@ -318,9 +318,9 @@ static int sm_count() {
   return n;
 }
 
-static void split_plan(int64_t n_rank, int64_t n_items_range, int* n_splits, int* tiles_per_split) {
+void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_splits, int* tiles_per_split) {
   const int64_t m_tiles = (n_rank + BM - 1) / BM;
-  const int64_t n_tiles = (n_items_range + BN - 1) / BN;
+  const int64_t n_tiles = (n_items_range + bn - 1) / bn;
   int64_t want = (2ll * sm_count() + m_tiles - 1) / m_tiles;  // aim for >= 2 CTAs per SM
   if (want < 1) want = 1;
   if (want > n_tiles) want = n_tiles;
@@ -330,6 +330,14 @@ static void split_plan(int64_t n_rank, int64_t n_items_range, int* n_splits, int
   *n_splits = (int)((n_tiles + *tiles_per_split - 1) / *tiles_per_split);
   if (*n_splits < 1) *n_splits = 1;
 }
+
+// tensor-core path (eval_tc.cu)
+bool eval_tc_eligible(int64_t K, int32_t k);
+int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, int n_splits);
+int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
+                 int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K,
+                 int64_t item_begin, int64_t item_end, int32_t k, void* d_workspace, int64_t workspace_bytes, int* n_splits_out,
+                 int** part_ids_out, float** part_scores_out, cudaStream_t s);
 
 static int mask_fields(const tgcn_graph* g, const int** rowptr, const int** col, int* row_begin, int* col_off) {
   if (g) {
@@ -353,11 +361,17 @@ using namespace tgcn;
 
 extern "C" {
 
-int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int32_t k) {
-  if (n_rank <= 0 || n_items_range <= 0 || k <= 0) return -1;
+int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k) {
+  if (n_rank <= 0 || n_items_range <= 0 || k <= 0 || K <= 0) return -1;
   int ns, tps;
-  split_plan(n_rank, n_items_range, &ns, &tps);
-  return (int64_t)ns * n_rank * k * 8 + 512;
+  eval_split_plan(n_rank, n_items_range, BN, &ns, &tps);
+  int64_t need = (int64_t)ns * n_rank * k * 8 + 512;
+  if (eval_tc_eligible(K, k)) {
+    eval_split_plan(n_rank, n_items_range, K <= 64 ? 256 : 128, &ns, &tps);
+    const int64_t tc = eval_tc_workspace_bytes(n_rank, n_items_range, K, k, ns);
+    if (tc > need) need = tc;
+  }
+  return need;
 }
 
 int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_t* d_users, int32_t n_parts, int32_t k,
@@ -384,16 +398,33 @@ int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_
 
 int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users, const float* d_user_vecs,
                    int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin, int64_t item_end,
-                   const float* d_user_bias, const float* d_item_bias, int32_t vecs_by_position, int32_t k, int32_t finalize,
-                   int32_t* d_out_ids, float* d_out_scores, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream) {
+                   const float* d_user_bias, const float* d_item_bias, int32_t vecs_by_position, int32_t precision, int32_t k,
+                   int32_t finalize, int32_t* d_out_ids, float* d_out_scores, void* d_workspace, int64_t workspace_bytes,
+                   tgcn_stream_t stream) {
   TGCN_REQUIRE(n_rank > 0 && K > 0 && K % 4 == 0 && ldu % 4 == 0 && ldi % 4 == 0 && ldu >= K && ldi >= K,
                "bad shapes: n_rank=%lld K=%lld ldu=%lld ldi=%lld (K, ld multiples of 4)", (long long)n_rank, (long long)K, (long long)ldu, (long long)ldi);
   TGCN_REQUIRE(item_begin >= 0 && item_end > item_begin && item_end < (1ll << 31), "bad item range [%lld, %lld)", (long long)item_begin, (long long)item_end);
   TGCN_REQUIRE(k > 0 && k <= TGCN_MAX_TOPK, "k=%d out of range (1..%d)", k, TGCN_MAX_TOPK);
   TGCN_REQUIRE(d_user_vecs && d_item_vecs && d_out_ids && d_out_scores, "NULL argument");
   TGCN_REQUIRE(((uintptr_t)d_user_vecs % 16 == 0) && ((uintptr_t)d_item_vecs % 16 == 0), "vector tables must be 16-byte aligned");
-  const int64_t need = tgcn_eval_workspace_bytes(n_rank, item_end - item_begin, k);
+  TGCN_REQUIRE(precision >= 0 && precision <= 2, "precision must be 0 (auto), 1 (fp32) or 2 (3xTF32)");
+  const int64_t need = tgcn_eval_workspace_bytes(n_rank, item_end - item_begin, K, k);
   TGCN_REQUIRE(d_workspace && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
+  const bool tc_ok = eval_tc_eligible(K, k) && !d_user_bias && !d_item_bias && ldu % 4 == 0 && ldi % 4 == 0;
+  TGCN_REQUIRE(precision != 2 || tc_ok, "3xTF32 path needs K %% 32 == 0, K <= 128, no bias terms and a k that fits shared memory");
+  if (tc_ok && precision != 1) {
+    const int* mrowptr;
+    const int* mcol;
+    int mrow_begin, mcol_off, n_splits;
+    int* part_ids;
+    float* part_scores;
+    if (int rc = mask_fields(mask_graph, &mrowptr, &mcol, &mrow_begin, &mcol_off)) return rc;
+    if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs,
+                              ldi, K, item_begin, item_end, k, d_workspace, workspace_bytes, &n_splits, &part_ids, &part_scores,
+                              (cudaStream_t)stream))
+      return rc;
+    return tgcn_topk_merge(mask_graph, n_rank, d_users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, stream);
+  }
   EvalArgs a;
   a.users = d_users;
   a.n_rank = (int)n_rank;
@@ -410,7 +441,7 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
   if (int rc = mask_fields(mask_graph, &a.mrowptr, &a.mcol, &a.mrow_begin, &a.mcol_off)) return rc;
   a.k = k;
   int n_splits;
-  split_plan(n_rank, item_end - item_begin, &n_splits, &a.tiles_per_split);
+  eval_split_plan(n_rank, item_end - item_begin, BN, &n_splits, &a.tiles_per_split);
   a.part_ids = (int*)d_workspace;
   a.part_scores = (float*)((char*)d_workspace + (size_t)n_splits * n_rank * k * 4);
   const size_t smem = (size_t)(BK * (BM + PAD) + BK * (BN + PAD)) * 4 + (size_t)BM * k * 8 + BM * 4;

@@ -133,6 +133,7 @@ class B200HotPath:
     """Mixin holding the kernel-backed overrides of BaseModel's hot-path methods."""
 
     dropout_rng = "host"  # "host": torch.rand on the CPU generator like base_model.py:82; "device": CUDA generator
+    eval_precision = "auto"  # "fp32" = exact FMA kernel; "3xtf32" = tcgen05 tensor cores; "auto" = 3xTF32 when eligible
 
     # -- graph ---------------------------------------------------------------------------------
     @property
@@ -221,7 +222,7 @@ class B200HotPath:
     def _rank(self, emb: torch.Tensor, users: torch.Tensor, k: int):
         """Fused score + mask + top-k for LightGCN scoring: user/item vectors are rows of the (N, d) table."""
         nu = self.n_users
-        return ops.eval_topk(self.graph, emb[:nu], emb[nu:], k, users=users)
+        return ops.eval_topk(self.graph, emb[:nu], emb[nu:], k, users=users, precision=self.eval_precision)
 
     @torch.no_grad()
     def predict_device(self, users, k: Optional[int] = None):
@@ -303,6 +304,7 @@ class BaseModel(B200HotPath, nn.Module):
             self.layer_combination = self.layer_combination_single
         self.fused_adam = getattr(params, "fused_adam", False)
         self.dropout_rng = getattr(params, "dropout_rng", "host")
+        self.eval_precision = getattr(params, "eval_precision", "auto")
 
     def _copy_dataset_params(self, dataset):
         self.n_users = dataset.n_users

@@ -22,7 +22,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _chk(t: torch.Tensor, dtype, name: str, dims: Optional[int] = None) -> torch.Tensor:
+def _chk(t: torch.Tensor, dtype, name: str, dims: Optional[int] = None, align: int = 16) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise _lib.TgcnError(f"{name} must be a CUDA tensor (textgcn_b200 has no CPU path)")
     if t.dtype != dtype:
@@ -31,8 +31,8 @@ def _chk(t: torch.Tensor, dtype, name: str, dims: Optional[int] = None) -> torch
         raise _lib.TgcnError(f"{name} must be contiguous")
     if dims is not None and t.dim() != dims:
         raise _lib.TgcnError(f"{name} must have {dims} dims, got {t.dim()}")
-    if t.data_ptr() % 16 != 0:
-        raise _lib.TgcnError(f"{name} must be 16-byte aligned")
+    if t.data_ptr() % align != 0:
+        raise _lib.TgcnError(f"{name} must be {align}-byte aligned")
     return t
 
 
@@ -50,9 +50,9 @@ class Graph:
                  row_begin: int = 0, block: bool = False):
         self.lib = _lib.load()
         self.n_users, self.n_items = int(n_users), int(n_items)
-        self.rowptr = _chk(rowptr, torch.int32, "rowptr", 1)
-        self.col = _chk(col, torch.int32, "col", 1)
-        self.val = _chk(val, torch.float32, "val", 1)
+        self.rowptr = _chk(rowptr, torch.int32, "rowptr", 1, align=4)  # CSR arrays are read with scalar loads
+        self.col = _chk(col, torch.int32, "col", 1, align=4)
+        self.val = _chk(val, torch.float32, "val", 1, align=4)
         self.nnz = int(col.numel())
         self.block = bool(block)
         self.row_begin = int(row_begin)
@@ -236,7 +236,7 @@ def bpr_fwd_bwd(n_users: int, n_items: int, emb: torch.Tensor, user_w: torch.Ten
     lib = _lib.load()
     _chk(emb, torch.float32, "emb", 2)
     d = emb.shape[1]
-    users, pos, negs = (_chk(t, torch.int32, n) for t, n in ((users, "users"), (pos, "pos"), (negs, "negs")))
+    users, pos, negs = (_chk(t, torch.int32, n, align=4) for t, n in ((users, "users"), (pos, "pos"), (negs, "negs")))
     batch = users.numel()
     n_neg = negs.numel() // batch
     losses = torch.empty(2, dtype=torch.float32, device=emb.device)
@@ -251,12 +251,13 @@ def bpr_fwd_bwd(n_users: int, n_items: int, emb: torch.Tensor, user_w: torch.Ten
 def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: torch.Tensor, k: int,
               users: Optional[torch.Tensor] = None, n_rank: Optional[int] = None,
               item_range: Optional[Tuple[int, int]] = None, user_bias: Optional[torch.Tensor] = None,
-              item_bias: Optional[torch.Tensor] = None, finalize: bool = True, by_position: bool = False
-              ) -> Tuple[torch.Tensor, torch.Tensor]:
+              item_bias: Optional[torch.Tensor] = None, finalize: bool = True, by_position: bool = False,
+              precision: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused score + mask + top-k.  Returns (ids (n_rank, k) int32, scores (n_rank, k) fp32).
 
     ``users`` (int32 ids) selects the rows to rank and whose train items are masked; with ``by_position`` the
-    user vectors / bias are already packed in list order (row m belongs to users[m])."""
+    user vectors / bias are already packed in list order (row m belongs to users[m]).
+    ``precision``: "fp32" (exact FMA, SIMT kernel), "3xtf32" (tcgen05 tensor cores) or "auto" (3xTF32 when eligible)."""
     lib = _lib.load()
     _chk(user_vecs, torch.float32, "user_vecs", 2)
     _chk(item_vecs, torch.float32, "item_vecs", 2)
@@ -264,7 +265,7 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
     if item_vecs.shape[1] != K:
         raise _lib.TgcnError("user and item vectors differ in width")
     if users is not None:
-        users = _chk(users, torch.int32, "users", 1)
+        users = _chk(users, torch.int32, "users", 1, align=4)
         n_rank = users.numel()
     elif n_rank is None:
         n_rank = user_vecs.shape[0]
@@ -272,14 +273,15 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
     dev = user_vecs.device
     ids = torch.empty((n_rank, k), dtype=torch.int32, device=dev)
     scores = torch.empty((n_rank, k), dtype=torch.float32, device=dev)
-    nbytes = int(lib.tgcn_eval_workspace_bytes(n_rank, i1 - i0, k))
+    prec = {"auto": 0, "fp32": 1, "3xtf32": 2}[precision]
+    nbytes = int(lib.tgcn_eval_workspace_bytes(n_rank, i1 - i0, K, k))
     if nbytes < 0:
         raise _lib.TgcnError("bad eval shape")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib.tgcn_eval_topk(mask_graph.handle if mask_graph is not None else None, n_rank, _ptr(users),
                                  _ptr(user_vecs), user_vecs.stride(0), _ptr(item_vecs), item_vecs.stride(0), K, i0, i1,
-                                 _ptr(user_bias), _ptr(item_bias), int(by_position), k, int(finalize), _ptr(ids), _ptr(scores),
+                                 _ptr(user_bias), _ptr(item_bias), int(by_position), prec, k, int(finalize), _ptr(ids), _ptr(scores),
                                  _ptr(ws), ws.numel(), _stream()))
     return ids, scores
 
@@ -303,8 +305,8 @@ def adv_select(g: Graph, emb: torch.Tensor, users: torch.Tensor, cands: torch.Te
                want_scores: bool = False):
     """Hardest-negative selection.  Returns (negs (B, kmax) int32 -1 padded, counts (B,), scores or None)."""
     _chk(emb, torch.float32, "emb", 2)
-    users = _chk(users, torch.int32, "users", 1)
-    cands = _chk(cands, torch.int32, "cands", 2)
+    users = _chk(users, torch.int32, "users", 1, align=4)
+    cands = _chk(cands, torch.int32, "cands", 2, align=4)
     b, c = cands.shape
     negs = torch.empty((b, kmax), dtype=torch.int32, device=emb.device)
     counts = torch.empty(b, dtype=torch.int32, device=emb.device)
@@ -323,7 +325,7 @@ def ltr_pairwise_features(n_users: int, emb, users, items, users_rev, users_desc
     out = torch.empty((b, n_feat), dtype=torch.float32, device=emb.device)
     with torch.cuda.device(emb.device):
         check(lib.tgcn_ltr_pairwise_features(n_users, emb.shape[1], users_rev.shape[1], b, n_feat,
-                                             _ptr(_chk(users, torch.int32, "users")), _ptr(_chk(items, torch.int32, "items")),
+                                             _ptr(_chk(users, torch.int32, "users", align=4)), _ptr(_chk(items, torch.int32, "items", align=4)),
                                              _ptr(_chk(emb, torch.float32, "emb")), _ptr(_chk(users_rev, torch.float32, "users_rev")),
                                              _ptr(_chk(users_desc, torch.float32, "users_desc")),
                                              _ptr(_chk(items_rev, torch.float32, "items_rev")),

@@ -13,9 +13,11 @@
 //   * Accumulators: 2 × BN TMEM columns (double buffered): the epilogue of tile t overlaps the MMAs of tile t+1.
 //   * Epilogue: TMEM lane = user row, so each of the 128 epilogue threads owns one user: it reads its row with
 //     tcgen05.ld (32 columns per instruction), compares every score against its k-th best (one FSETP per score)
-//     and only on a hit checks the train mask (binary search in the user row of Â) and inserts into its private
-//     sorted list in shared memory.  Items arrive in increasing id order, so a strict '>' keeps the canonical
-//     (score desc, id asc) order.
+//     tcgen05.ld (32 columns per instruction), builds a branch-free 32-bit hit mask against its k-th best (one
+//     FSETP per score) and only for set bits consults a 128-bit register Bloom filter of the user's train items
+//     (exact binary search in the user row of Â only when the bit is set) and inserts into its private sorted
+//     list, which lives in REGISTERS (shift-insert, ~6 instructions per entry, no memory).  Items arrive in
+//     increasing id order, so a strict '>' keeps the canonical (score desc, id asc) order.
 //
 // Roofline: tensor pipe, 3 × 2·K TF32 flops per score (MMA floor 128 cycles per 128×256×8 instruction).
 #include <cuda.h>
@@ -27,7 +29,6 @@
 namespace tgcn {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
 constexpr int TC_CHUNK = 32;            // fp32 per 128-byte swizzle row
 constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
 constexpr int TC_MAX_STAGES = 8;
@@ -119,24 +120,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Thread-private insert into a descending list stored with stride 128 (one column of a [k][128] array).
-__device__ __noinline__ float thread_list_insert(float* ls, int* li, int k, float s, int id) {
-  int j = k - 1;
-  while (j > 0) {
-    const float ps = ls[(j - 1) * TC_BM];
-    const int pi = li[(j - 1) * TC_BM];
-    if (!ranks_before(s, id, ps, pi)) break;
-    ls[j * TC_BM] = ps;
-    li[j * TC_BM] = pi;
-    --j;
-  }
-  ls[j * TC_BM] = s;
-  li[j * TC_BM] = id;
-  return ls[(k - 1) * TC_BM];
+// ---- per-thread top-k list held in REGISTERS (KL entries, sorted best-first) ------------------------------------
+// v[j] for a run-time j without spilling v[] to local memory: 31 selects.
+__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
+  uint32_t r = v[0];
+#pragma unroll
+  for (int i = 1; i < 32; ++i) r = (j == i) ? v[i] : r;
+  return __uint_as_float(r);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Insert (s, id) into the sorted list: once the insertion point is passed every later entry shifts down by one
+// (carried in s/id); the last carried entry falls off.  Pure register traffic: ~6 instructions per entry.
+// Candidates arrive in increasing id order, so on equal scores the earlier entry stays ahead ('>' is strict).
+template <int KL>
+__device__ __forceinline__ void reg_list_insert(float (&ls)[KL], int (&li)[KL], float s, int id) {
+  bool shifting = false;
+#pragma unroll
+  for (int j = 0; j < KL; ++j) {
+    shifting = shifting || ranks_before(s, id, ls[j], li[j]);
+    const float ts = ls[j];
+    const int ti = li[j];
+    ls[j] = shifting ? s : ts;
+    li[j] = shifting ? id : ti;
+    s = shifting ? ts : s;
+    id = shifting ? ti : id;
+  }
+}
+
+// BN = item rows per tile, KL = list capacity (>= k), EW = epilogue warps per TMEM lane quarter.  With EW = 2 the two
+// warps of a quarter read the same 32 lanes but own 16 user rows each, which halves the chain of (warp-serialised)
+// list updates — the epilogue's critical path, since hits are rare but divergent.
+template <int BN, int KL, int EW>
+__global__ void __launch_bounds__(128 + 128 * EW, 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
@@ -146,10 +161,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   constexpr int B_STAGE_BYTES = BN * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
-  uint8_t* gen_lists = gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES;
-  float* list_s = reinterpret_cast<float*>(gen_lists);        // [k][128]
-  int* list_i = reinterpret_cast<int*>(list_s + a.k * TC_BM);  // [k][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(list_i + a.k * TC_BM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES);
   const uint32_t bar_a_full = smem_u32(bars + 0);
   const uint32_t bar_b_full = smem_u32(bars + 1);                      // [TC_MAX_STAGES]
   const uint32_t bar_b_empty = smem_u32(bars + 1 + TC_MAX_STAGES);     // [TC_MAX_STAGES]
@@ -175,20 +187,13 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
-      mbar_init(bar_t_empty + 8 * s, 4);  // one arrival per epilogue warp
+      mbar_init(bar_t_empty + 8 * s, 4 * EW);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 4) {
-    const int t = threadIdx.x - 128;
-    for (int j = 0; j < a.k; ++j) {
-      list_s[j * TC_BM + t] = -INFINITY;
-      list_i[j * TC_BM + t] = INT_MAX;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -261,19 +266,43 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue: one thread per user row ----
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // ---- epilogue: one thread per user row (EW warps share a lane quarter, 32 / EW rows each) ----
+    const int ew = warp & 3;         // the TMEM lane quarter this warp may read (warp id % 4)
+    const int sub = (warp - 4) >> 2;  // which slice of the quarter's 32 rows this warp owns
     const int t = ew * 32 + lane;
     const int m = m0 + t;
-    const bool valid = m < a.n_rank;
+    const bool mine = (lane / (32 / EW)) == sub;
+    const bool valid = mine && m < a.n_rank;
     const int user = valid ? (a.users ? __ldg(a.users + m) : m) : 0;
     int mlo = 0, mhi = 0;
     if (valid && a.mrowptr) {
       mlo = __ldg(a.mrowptr + user - a.mrow_begin);
       mhi = __ldg(a.mrowptr + user - a.mrow_begin + 1);
     }
-    float* ls = list_s + t;
-    int* li = list_i + t;
+    // 128-bit Bloom filter of the user's train items (bit = item id mod 128): the exact membership test (a binary
+    // search in global memory, ~1 us of dependent latency) only runs for candidates whose bit is set.
+    uint32_t bloom[4] = {0u, 0u, 0u, 0u};
+    for (int p = mlo; p < mhi; p += 4) {
+      int it[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) it[q] = p + q < mhi ? __ldg(a.mcol + p + q) - a.mcol_off : -1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (it[q] >= 0) {
+          const uint32_t b = (uint32_t)it[q] & 127u;
+          bloom[0] |= (b >> 5) == 0 ? 1u << (b & 31) : 0u;
+          bloom[1] |= (b >> 5) == 1 ? 1u << (b & 31) : 0u;
+          bloom[2] |= (b >> 5) == 2 ? 1u << (b & 31) : 0u;
+          bloom[3] |= (b >> 5) == 3 ? 1u << (b & 31) : 0u;
+        }
+    }
+    float ls[KL];
+    int li[KL];
+#pragma unroll
+    for (int j = 0; j < KL; ++j) {
+      ls[j] = -INFINITY;
+      li[j] = INT_MAX;
+    }
     float thr = -INFINITY;
     int as = 0;
     uint32_t aphase = 0;
@@ -285,14 +314,26 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       for (int g = 0; g < BN / 32; ++g) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + g * 32, v);
-        if (valid) {
-          const int nbase = n0 + g * 32;
+        const int nbase = n0 + g * 32;
+        // branch-free hit mask: one FSETP per score against the row's current k-th best
+        uint32_t hits = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(v[j]);
-            if (s > thr && nbase + j < a.n_range) {
-              const int item = a.item_begin + nbase + j;
-              if (!sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) thr = thread_list_insert(ls, li, a.k, s, item);
+        for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+        const int rem = a.n_range - nbase;  // columns past the item range hold zero-filled rows
+        if (rem < 32) hits &= rem > 0 ? (1u << rem) - 1u : 0u;
+        if (!valid) hits = 0;
+        while (hits) {  // rare and divergent: ~k·(1 + ln(n/k)) times per user over the whole sweep
+          const int j = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const float s = pick32(v, j);
+          if (s > thr) {
+            const int item = a.item_begin + nbase + j;
+            const uint32_t b = (uint32_t)item & 127u;
+            const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
+            const bool maybe = (word >> (b & 31)) & 1u;
+            if (!maybe || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
+              reg_list_insert<KL>(ls, li, s, item);
+              thr = ls[KL - 1];
             }
           }
         }
@@ -307,10 +348,12 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     }
     if (valid) {
       const size_t o = ((size_t)blockIdx.y * a.n_rank + m) * a.k;
-      for (int j = 0; j < a.k; ++j) {
-        a.part_ids[o + j] = li[j * TC_BM];
-        a.part_scores[o + j] = ls[j * TC_BM];
-      }
+#pragma unroll
+      for (int j = 0; j < KL; ++j)
+        if (j < a.k) {
+          a.part_ids[o + j] = li[j];
+          a.part_scores[o + j] = ls[j];
+        }
     }
   }
   tc_fence_before();
@@ -379,8 +422,7 @@ static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 static void tc_plan(int K, int k, int* bn, int* n_stages, size_t* smem) {
   *bn = K <= 64 ? 256 : 128;
   const size_t a_bytes = (size_t)(2 * (K / TC_CHUNK)) * TC_A_CHUNK_BYTES;
-  const size_t lists = (size_t)k * TC_BM * 8;
-  const size_t fixed = 1024 /*align slack*/ + a_bytes + lists + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
+  const size_t fixed = 1024 /*align slack*/ + a_bytes + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
   const size_t budget = 227 * 1024;
   const size_t stage = (size_t)*bn * 128;
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
@@ -390,7 +432,7 @@ static void tc_plan(int K, int k, int* bn, int* n_stages, size_t* smem) {
 }
 
 bool eval_tc_eligible(int64_t K, int32_t k) {
-  if (K % TC_CHUNK != 0 || K > 128 || K <= 0) return false;
+  if (K % TC_CHUNK != 0 || K > 128 || K <= 0 || k > 64) return false;  // register-resident lists: k <= 64
   int bn, st;
   size_t sm;
   tc_plan((int)K, k, &bn, &st, &sm);
@@ -445,13 +487,21 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   a.part_ids = part_ids;
   a.part_scores = part_scores;
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
+#define TGCN_TC_LAUNCH(BN_, KL_, EW_)                                                                                        \
+  do {                                                                                                                       \
+    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    eval_topk_tc_kernel<BN_, KL_, EW_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                               \
+  } while (0)
   if (bn == 256) {
-    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eval_topk_tc_kernel<256><<<grid, TC_THREADS, smem, s>>>(map_u, map_i, a);
+    if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2);
+    else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2);
+    else TGCN_TC_LAUNCH(256, 64, 1);
   } else {
-    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eval_topk_tc_kernel<128><<<grid, TC_THREADS, smem, s>>>(map_u, map_i, a);
+    if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2);
+    else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2);
+    else TGCN_TC_LAUNCH(128, 64, 1);
   }
+#undef TGCN_TC_LAUNCH
   TGCN_CHECK_LAUNCH();
   *n_splits_out = n_splits;
   *part_ids_out = part_ids;

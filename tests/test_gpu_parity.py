@@ -424,3 +424,70 @@ def test_full_size_eval_properties_and_sample_against_oracle(ops, electronics):
     empty_sc = torch.full_like(sc, float("-inf"))
     m_ids, m_sc = ops.topk_merge(e["graph"], torch.stack([empty_ids, ids]).contiguous(), torch.stack([empty_sc, sc]).contiguous())
     assert torch.equal(m_ids, ids) and torch.equal(m_sc, sc)
+
+
+def test_full_size_adv_select_config3(ops, electronics):
+    """BASELINE.json configs[2]: hardest-of-1000 negatives at the Electronics shape (B = 2048, k = 20)."""
+    e = electronics
+    emb = ops.propagate_fwd(e["graph"], e["uw"].to(DEV), e["iw"].to(DEV), 3)
+    rng = np.random.default_rng(1)
+    users = rng.integers(e["nu"], size=2048)
+    cands = np.stack([rng.choice(e["ni"], size=1000, replace=False) for _ in users])
+    negs, counts, scores = ops.adv_select(e["graph"], emb, ops.as_index(users, DEV), ops.as_index(cands, DEV), 20, want_scores=True)
+    negs, counts, scores = negs.cpu().numpy(), counts.cpu().numpy(), scores.cpu()
+    assert (counts == 20).all()
+    tl = O.train_lists_from_edges(e["tu"], e["ti"], e["nu"])
+    emb_c = emb.cpu()
+    ref_rank = O.adv_rank_candidates(emb_c[:e["nu"]], emb_c[e["nu"]:], torch.from_numpy(users), torch.from_numpy(cands))
+    assert rel_err(scores.numpy(), ref_rank.numpy()) < TOL
+    # selection logic exactly, given the kernel's own scores (removes fp summation-order noise from the comparison)
+    ref = O.adv_select_negatives(scores, torch.from_numpy(cands), users, tl, 20)
+    for b in range(len(users)):
+        assert np.array_equal(negs[b], ref[b])
+        assert not np.isin(negs[b], tl[users[b]]).any()
+
+
+def test_full_size_ltr_ranking_config4(ops, electronics):
+    """BASELINE.json configs[3]: LTR ranking with random 768-d text tables through the collapsed single contraction."""
+    e = electronics
+    from textgcn_b200.models import LTRLinearWPop, make_params
+    import logging
+    nu, ni, D = e["nu"], e["ni"], 768
+    gen = torch.Generator().manual_seed(4)
+
+    class DS:
+        pass
+
+    ds = DS()
+    ds.n_users, ds.n_items, ds.graph = nu, ni, e["graph"]
+    ds.norm_matrix = None
+    ds.test_users = np.arange(512)
+    ds.true_test_lil = [[0]] * 512
+    ds.items_as_avg_reviews = torch.randn(ni, D, generator=gen).to(DEV)
+    ds.items_as_desc = torch.randn(ni, D, generator=gen).to(DEV)
+    ds.users_as_avg_reviews = torch.randn(nu, D, generator=gen).to(DEV)
+    ds.users_as_avg_desc = torch.randn(nu, D, generator=gen).to(DEV)
+    ds.popularity_users = torch.rand(nu, 1, generator=gen).to(DEV)
+    ds.popularity_items = torch.rand(ni, 1, generator=gen).to(DEV)
+    model = LTRLinearWPop(make_params(k=[20], logger=logging.getLogger("t")), ds)
+    with torch.no_grad():
+        model.embedding_user.weight.copy_(e["uw"])
+        model.embedding_item.weight.copy_(e["iw"])
+    users = np.random.default_rng(2).choice(nu, 192, replace=False)
+    ids, sc = model.predict_device(users)
+    # oracle: the reference's 5 GEMMs + cat + Linear on the CPU, then mask + canonical top-k
+    emb = ops.propagate_fwd(e["graph"], e["uw"].to(DEV), e["iw"].to(DEV), 3).cpu()
+    tabs = {"users_rev": ds.users_as_avg_reviews.cpu(), "users_desc": ds.users_as_avg_desc.cpu(),
+            "items_rev": ds.items_as_avg_reviews.cpu(), "items_desc": ds.items_as_desc.cpu()}
+    ws = [l.weight.detach().cpu() for l in model.layers]
+    bs = [l.bias.detach().cpu() for l in model.layers]
+    ut = torch.from_numpy(users)
+    dense = O.ltr_score_batchwise(emb[:nu][ut], emb[nu:], ut, tabs, ws, bs,
+                                  (ds.popularity_users.cpu(), ds.popularity_items.cpu())).numpy()
+    tl = O.train_lists_from_edges(e["tu"], e["ti"], nu)
+    for r, u in enumerate(users):
+        dense[r, tl[u]] = -np.inf
+    o_ids, o_sc = O.canonical_topk(dense, 20)
+    scale = float(np.abs(dense[np.isfinite(dense)]).max())
+    st = O.topk_lists_equivalent(ids.cpu().numpy().astype(np.int64), sc.cpu().numpy(), o_ids, o_sc, rtol=0, atol=1.01e-4 + 2 * TOL * scale)
+    assert st["bad"] == 0 and st["exact"] >= st["rows"] - 8, st

@@ -32,6 +32,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_CHUNK = 32;            // fp32 per 128-byte swizzle row
 constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
 constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_VSTRIDE = 36;           // floats per row of the hit staging area (32 + pad: conflict-free 128-bit stores)
 
 struct TcArgs {
   int n_rank, K, n_range, item_begin, k;
@@ -121,30 +122,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---- per-thread top-k list held in REGISTERS (KL entries, sorted best-first) ------------------------------------
-// v[j] for a run-time j without spilling v[] to local memory: 31 selects.
-__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
-  uint32_t r = v[0];
-#pragma unroll
-  for (int i = 1; i < 32; ++i) r = (j == i) ? v[i] : r;
-  return __uint_as_float(r);
-}
-
-// Insert (s, id) into the sorted list: once the insertion point is passed every later entry shifts down by one
-// (carried in s/id); the last carried entry falls off.  Pure register traffic: ~6 instructions per entry.
-// Candidates arrive in increasing id order, so on equal scores the earlier entry stays ahead ('>' is strict).
+// Insert (s, id): entry j takes its upper neighbour when s beats that neighbour, s itself when s beats only entry j.
+// Every entry is decided from the ORIGINAL values (walk bottom-up), so the KL updates are independent (high ILP,
+// ~5 instructions each, no memory).  Candidates arrive in increasing id order, so a strict '>' keeps the earlier
+// entry ahead on equal scores (canonical order).
 template <int KL>
 __device__ __forceinline__ void reg_list_insert(float (&ls)[KL], int (&li)[KL], float s, int id) {
-  bool shifting = false;
 #pragma unroll
-  for (int j = 0; j < KL; ++j) {
-    shifting = shifting || ranks_before(s, id, ls[j], li[j]);
-    const float ts = ls[j];
-    const int ti = li[j];
-    ls[j] = shifting ? s : ts;
-    li[j] = shifting ? id : ti;
-    s = shifting ? ts : s;
-    id = shifting ? ti : id;
+  for (int j = KL - 1; j >= 1; --j) {
+    const bool up = s > ls[j - 1];
+    const bool here = s > ls[j];
+    ls[j] = up ? ls[j - 1] : (here ? s : ls[j]);
+    li[j] = up ? li[j - 1] : (here ? id : li[j]);
   }
+  const bool top = s > ls[0];
+  ls[0] = top ? s : ls[0];
+  li[0] = top ? id : li[0];
 }
 
 // BN = item rows per tile, KL = list capacity (>= k), EW = epilogue warps per TMEM lane quarter.  With EW = 2 the two
@@ -161,7 +154,8 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   constexpr int B_STAGE_BYTES = BN * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES);
+  float* stage_v = reinterpret_cast<float*>(gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES);  // [128][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_v + TC_BM * TC_VSTRIDE);
   const uint32_t bar_a_full = smem_u32(bars + 0);
   const uint32_t bar_b_full = smem_u32(bars + 1);                      // [TC_MAX_STAGES]
   const uint32_t bar_b_empty = smem_u32(bars + 1 + TC_MAX_STAGES);     // [TC_MAX_STAGES]
@@ -315,27 +309,36 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + g * 32, v);
         const int nbase = n0 + g * 32;
-        // branch-free hit mask: one FSETP per score against the row's current k-th best
+        // hit mask: one FSETP + one predicated OR per score against the row's current k-th best
         uint32_t hits = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+        for (int j = 0; j < 32; ++j)
+          if (__uint_as_float(v[j]) > thr) hits |= 1u << j;
         const int rem = a.n_range - nbase;  // columns past the item range hold zero-filled rows
         if (rem < 32) hits &= rem > 0 ? (1u << rem) - 1u : 0u;
         if (!valid) hits = 0;
-        while (hits) {  // rare and divergent: ~k·(1 + ln(n/k)) times per user over the whole sweep
-          const int j = __ffs(hits) - 1;
-          hits &= hits - 1;
-          const float s = pick32(v, j);
-          if (s > thr) {
-            const int item = a.item_begin + nbase + j;
-            const uint32_t b = (uint32_t)item & 127u;
-            const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
-            const bool maybe = (word >> (b & 31)) & 1u;
-            if (!maybe || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
-              reg_list_insert<KL>(ls, li, s, item);
-              thr = ls[KL - 1];
+        if (hits) {  // rare and divergent: ~k·(1 + ln(n/k)) candidates per user over the whole sweep
+          // park the 32 scores in this row's private shared-memory slot so a run-time column can be read back
+          float4* sv = reinterpret_cast<float4*>(stage_v + t * TC_VSTRIDE);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            sv[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                __uint_as_float(v[4 * q + 3]));
+          do {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const float s = stage_v[t * TC_VSTRIDE + j];
+            if (s > thr) {
+              const int item = a.item_begin + nbase + j;
+              const uint32_t b = (uint32_t)item & 127u;
+              const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
+              const bool maybe = (word >> (b & 31)) & 1u;
+              if (!maybe || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
+                reg_list_insert<KL>(ls, li, s, item);
+                thr = ls[KL - 1];
+              }
             }
-          }
+          } while (hits);
         }
       }
       tc_fence_before();
@@ -422,7 +425,7 @@ static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 static void tc_plan(int K, int k, int* bn, int* n_stages, size_t* smem) {
   *bn = K <= 64 ? 256 : 128;
   const size_t a_bytes = (size_t)(2 * (K / TC_CHUNK)) * TC_A_CHUNK_BYTES;
-  const size_t fixed = 1024 /*align slack*/ + a_bytes + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
+  const size_t fixed = 1024 /*align slack*/ + a_bytes + (size_t)TC_BM * TC_VSTRIDE * 4 + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
   const size_t budget = 227 * 1024;
   const size_t stage = (size_t)*bn * 128;
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;

@@ -185,21 +185,30 @@ class BipartitePropagator:
         """e0_user_local: owned rows of the user table; e0_item: the whole item table (identical on every rank).
         Writes this rank's rows of users_emb and the whole items_emb."""
         L = self.n_layers
-        cur_u, cur_i = e0_user_local, e0_item
+        ws = self.part.world_size
+
+        def reduce_async(t):
+            return dist.all_reduce(t, group=self.group, async_op=True) if ws > 1 else None
+
+        # Software pipeline: the all-reduce of layer l's item table (AR_l) only feeds the USER rows of layer l+1, so it
+        # runs behind two local SpMMs: A_l (user rows of layer l, needs AR_{l-1}) and B_{l+1} (item partials of layer
+        # l+1, needs A_l's output).  Compute per hop = A + B back to back; the collective is hidden behind it.
+        self.spmm_fn(self.ig, e0_user_local, self.ibufs[0], [], 1.0)       # B_1: partial item rows of layer 1
+        work = reduce_async(self.ibufs[0])
+        cur_i = e0_item
         for layer in range(1, L + 1):
             last = layer == L
-            part_i = self.ibufs[layer - 1]
-            self.spmm_fn(self.ig, cur_u, part_i, [], 1.0)                 # partial item rows over owned users
-            work = dist.all_reduce(part_i, group=self.group, async_op=True) if self.part.world_size > 1 else None
-            if last:                                                        # user rows: local, overlaps the all-reduce
+            if last:                                                        # A_l: user rows of layer l (local)
                 adds = [] if single else [e0_user_local] + self.ubufs
                 self.spmm_fn(self.ug, cur_i, out_user_local, adds, 1.0 if single else float(L + 1))
             else:
                 self.spmm_fn(self.ug, cur_i, self.ubufs[layer - 1], [], 1.0)
-                cur_u = self.ubufs[layer - 1]
+                self.spmm_fn(self.ig, self.ubufs[layer - 1], self.ibufs[layer], [], 1.0)   # B_{l+1}
             if work is not None:
-                work.wait()
-            cur_i = part_i
+                work.wait()                                                 # item table of layer l is complete
+            cur_i = self.ibufs[layer - 1]
+            if not last:
+                work = reduce_async(self.ibufs[layer])
         if single:
             out_item.copy_(cur_i)
         else:

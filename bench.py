@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--mg-scheme", default="bipartite", choices=["bipartite", "rowblock"],
                     help="multi-GPU propagation: users partitioned + item-table all-reduce, or row blocks + all-gather")
@@ -134,6 +135,48 @@ def timed_steps(fn, steps, warmup, flush, torch):
     return [s.elapsed_time(e) for s, e in ev]
 
 
+def make_batch(w, batch, device, torch, seed=1):
+    """(B, 3) int64 rows [user, positive, negative]: a random train interaction per row + a uniform random item."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    e = torch.randint(0, int(w["rowptr"][w["nu"]]), (batch,), generator=gen, device=device)
+    users = torch.searchsorted(w["rowptr"][:w["nu"] + 1].to(torch.int64), e, right=True) - 1
+    pos = w["col"][e].to(torch.int64) - w["nu"]
+    neg = torch.randint(0, w["ni"], (batch,), generator=gen, device=device)
+    return torch.stack([users, pos, neg], dim=1)
+
+
+def train_leg(w, graph, dev, flush, torch, batch=2048, steps=10, warmup=3):
+    import logging
+    from textgcn_b200.models import BaseModel, make_params
+
+    class DS:
+        pass
+
+    ds = DS()
+    ds.n_users, ds.n_items, ds.graph, ds.norm_matrix = w["nu"], w["ni"], graph, None
+    ds.test_users, ds.true_test_lil = [0], [[0]]
+    params = make_params(emb_size=w["d"], n_layers=w["L"], k=[20], batch_size=batch, fused_adam=True, dropout_rng="device",
+                         device=dev, logger=logging.getLogger("bench"))
+    model = BaseModel(params, ds)
+    from textgcn_b200.optim import FusedAdam
+    opt = FusedAdam(model.parameters(), lr=params.lr)
+    data = make_batch(w, batch, dev, torch)
+    model.train()
+    model.training = True
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss = model.get_loss(data)
+        loss.backward()
+        opt.step()
+
+    t = timed_steps(step, steps, warmup, flush, torch)
+    ms = sum(t) / len(t)
+    return {"ms_per_step": ms, "batch": batch, "dropout": params.dropout, "steps_per_s": 1e3 / ms,
+            "includes": "device dropout draw, L-layer propagate, fused BPR(SELU)+L2 kernel, Horner backward (L transposed SpMM), "
+                        "fused Adam over both tables"}
+
+
 def cpu_baseline(w, topk, n_predict=2048):
     """The reference's CPU path (oracle port: torch.sparse.mm x L + mean; matmul + mask + topk) on the host cores."""
     import numpy as np
@@ -158,7 +201,12 @@ def cpu_baseline(w, topk, n_predict=2048):
     t = time.perf_counter()
     O.predict_topk_torch(ue, ie, users, train_lists, topk)
     t_pred = time.perf_counter() - t
-    return {"value": w["nnz"] * w["L"] / best, "unit": "edges/s", "cores": cores, "kind": "port",
+    batch = make_batch(w, 2048, "cpu" if not w["rowptr"].is_cuda else w["rowptr"].device, torch).cpu()
+    keep = torch.rand(norm._nnz()) < 0.6
+    t = time.perf_counter()
+    O.train_step_loss_and_grads(norm, uw, iw, w["L"], batch, 1e-4, keep_mask=keep, dropout=0.4)
+    t_train = time.perf_counter() - t
+    return {"value": w["nnz"] * w["L"] / best, "unit": "edges/s", "cores": cores, "kind": "port", "train_ms_per_step": t_train * 1e3,
             "sample": f"full {w['name']} representation ({w['L']} x torch.sparse.mm + mean), best of 3 = {best * 1e3:.1f} ms; "
                       f"predict on {len(users)} users = {t_pred * 1e3:.1f} ms",
             "eval_users_per_s": len(users) / t_pred, "ms_per_step": best * 1e3}
@@ -443,6 +491,13 @@ def main():
             ev["e2e_d2h_bytes"] = n_eval * k * 8
     sampler.stop_flag = True
     sampler.join(timeout=1)
+
+    # ---- training step (a7-a10): dropout draw + propagate + fused BPR + Horner backward + fused Adam ---------
+    if world == 1 and not args.no_train:
+        try:
+            extra["train"] = train_leg(w, graph, dev, flush, torch)
+        except Exception as exc:
+            extra["train"] = {"error": str(exc)[:300]}
 
     # ---- same workload on ONE GPU, measured by rank 0 in the same run (for honest strong-scaling ratios) ----
     if world > 1 and rank == 0:

@@ -178,6 +178,13 @@ int tgcn_ltr_pack_users(int64_t n_rank, const int32_t* d_users, int64_t d, int64
                         const float* d_users_emb, const float* d_users_rev, const float* d_users_desc,
                         float* d_out, tgcn_stream_t stream);
 
+/* n1 (next row)  GPU negative sampler replacing BaseDataset._cache_samples / __getitem__ (dataset.py:167-193):
+ * for each of `batch` user ids writes the int64 row [user, uniform positive, n_neg uniform non-positive items
+ * (distinct within the row)] into d_out (batch, 2 + n_neg).  Counter-based RNG keyed by (seed, row).  Rows for which
+ * no negative exists get -1 and bump *d_fail_count (the reference loops forever there). */
+int tgcn_sample_bpr_batch(const tgcn_graph_t* g, int64_t batch, int32_t n_neg, const int32_t* d_users, uint64_t seed,
+                          int32_t max_tries, int64_t* d_out, int32_t* d_fail_count, tgcn_stream_t stream);
+
 /* n3 (next row)  dense Adam step over one table, torch.optim.Adam defaults (base_model.py:111, :126):
  * p, m, v updated in place from g; step is the 1-based step count. */
 int tgcn_adam_step(int64_t n, float* d_p, const float* d_g, float* d_m, float* d_v, float lr, float beta1,

@@ -491,3 +491,43 @@ def test_full_size_ltr_ranking_config4(ops, electronics):
     scale = float(np.abs(dense[np.isfinite(dense)]).max())
     st = O.topk_lists_equivalent(ids.cpu().numpy().astype(np.int64), sc.cpu().numpy(), o_ids, o_sc, rtol=0, atol=1.01e-4 + 2 * TOL * scale)
     assert st["bad"] == 0 and st["exact"] >= st["rows"] - 8, st
+
+
+def test_gpu_sampler_properties_and_fit(ops):
+    """n1: the GPU BPR sampler yields valid rows (positive in the user's train list, negatives outside it and distinct)
+    with roughly uniform negatives, terminates on a user who interacted with almost every item (G20), and drives fit()."""
+    from textgcn_b200.models import BaseModel
+    from textgcn_b200.sampler import BprEpochSampler
+    g = load_golden("small_lgcn_d64")
+    gr = _graph(ops, g)
+    tl = golden_lists(g)
+    smp = BprEpochSampler(gr, batch_size=64, neg_samples=3, seed=7)
+    rows = torch.cat(list(smp)).cpu().numpy()
+    assert rows.shape == (smp.rows, 5) and len(smp) == (smp.rows + 63) // 64
+    assert np.array_equal(np.bincount(rows[:, 0], minlength=gr.n_users), np.full(gr.n_users, smp.bucket_len))
+    for u, p, *negs in rows:
+        assert p in tl[u] and len(set(negs)) == 3 and not np.isin(negs, tl[u]).any()
+    counts = np.bincount(rows[:, 2:].ravel(), minlength=gr.n_items)
+    assert counts.min() > 0 and counts.max() < 4 * counts.mean()          # every item gets sampled, no gross skew
+    assert int(smp.fail_count) == 0
+    rows2 = torch.cat(list(BprEpochSampler(gr, batch_size=64, neg_samples=3, seed=7))).cpu().numpy()
+    assert np.array_equal(rows, rows2)                                      # reproducible from the seed
+    # dummy user 0 has 3 of 4 items: one negative exists, three cannot -> bounded, reported, no hang
+    gd = load_golden("dummy_lgcn")
+    grd = _graph(ops, gd)
+    s1 = BprEpochSampler(grd, batch_size=8, neg_samples=1, seed=0)
+    r1 = torch.cat(list(s1)).cpu().numpy()
+    assert (r1[r1[:, 0] == 0][:, 2] == 3).all() and int(s1.fail_count) == 0
+    s3 = BprEpochSampler(grd, batch_size=8, neg_samples=3, seed=0)
+    r3 = torch.cat(list(s3)).cpu().numpy()
+    assert (r3[r3[:, 0] == 0][:, 3:] == -1).all() and int(s3.fail_count) > 0
+    # end to end: fit() over the sampler reduces the training loss
+    model = BaseModel(params_from_golden(g, epochs=3, evaluate_every=3, lr=5e-3, fused_adam=True, dropout_rng="device"), StubDataset(g, DEV))
+    load_weights(model, g)
+    batch = torch.from_numpy(g["batch"][:, :3])
+    model._loss_values = {"bpr": 0.0, "reg": 0.0}
+    before = float(model.get_loss(batch))
+    model.fit(BprEpochSampler(gr, batch_size=256, neg_samples=1, seed=1))
+    model.training = False
+    model._loss_values = {"bpr": 0.0, "reg": 0.0}
+    assert float(model.get_loss(batch)) < before

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--topk", type=int, default=20)
+    ap.add_argument("--no-l2-hints", action="store_true", help="disable the L2 cache-policy hints of the SpMM (A/B comparison)")
     ap.add_argument("--mg-scheme", default="bipartite", choices=["bipartite", "rowblock"],
                     help="multi-GPU propagation: users partitioned + item-table all-reduce, or row blocks + all-gather")
     return ap.parse_args()
@@ -296,6 +297,8 @@ def main():
     extra = {}
     if world == 1:
         graph = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
+        if args.no_l2_hints:
+            graph.set_hot_rows(-1)
         out = torch.empty((n, d), dtype=torch.float32, device=dev)
 
         def step():
@@ -332,6 +335,7 @@ def main():
         u0, u1 = part.users(rank)
         ugraph = ops.Graph(nu, ni, *part.user_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=u0, block=True)
         ugraph.set_mask_col_offset(0)
+        ugraph.set_hot_rows(u1 - u0)  # every row of this block gathers from the replicated item table: keep it in L2
         igraph = ops.Graph(nu, ni, *part.item_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=nu, block=True)
         prop = tdist.BipartitePropagator(part, rank, ugraph, igraph, d, L, dev)
         e0_u = w["uw"][u0:u1].contiguous()

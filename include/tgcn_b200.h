@@ -60,6 +60,10 @@ int64_t tgcn_graph_num_segments(const tgcn_graph_t* g);
 /* Eval masks read the user rows of a handle: local row = user id - row_begin, an entry equals col_offset + item id.
  * col_offset defaults to n_users (global column numbering); a row block whose columns are item ids sets 0. */
 int tgcn_graph_set_mask_col_offset(tgcn_graph_t* g, int64_t col_offset);
+/* L2 cache-policy hints for tables larger than L2: rows [0, hot_rows) of the handle gather from the small skewed
+ * table (the item table) whose lines are kept with evict_last; everything else streams with evict_first.  Defaults:
+ * whole graph = n_users, row block = 0.  hot_rows = -1 disables the hints. */
+int tgcn_graph_set_hot_rows(tgcn_graph_t* g, int64_t hot_rows);
 /* bytes of caller-provided workspace for propagate_fwd / propagate_bwd */
 int64_t tgcn_propagate_workspace_bytes(const tgcn_graph_t* g, int64_t d, int32_t n_layers);
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "tgcn_graph_destroy": (None, [_P]),
     "tgcn_graph_num_segments": (c_int64, [_P]),
     "tgcn_graph_set_mask_col_offset": (c_int32, [_P, c_int64]),
+    "tgcn_graph_set_hot_rows": (c_int32, [_P, c_int64]),
     "tgcn_propagate_workspace_bytes": (c_int64, [_P, c_int64, c_int32]),
     "tgcn_spmm_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, _P]),
     "tgcn_spmm_ex": (c_int32, [_P, c_int64, _P, _P, _P, c_float, c_int32, c_int32, POINTER(c_void_p), POINTER(c_void_p),

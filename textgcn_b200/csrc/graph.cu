@@ -152,6 +152,8 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->n_segments = g->n_split_rows = 0;
   g->bipartite = 0;
   g->mask_col_off = (int)n_users;
+  g->l2_hints = 1;
+  g->hot_rows = is_block ? 0 : (int)n_users;
   int rc = build_segments(g, (cudaStream_t)stream);
   if (rc == 0 && nnz > 0) rc = check_rows(g, (cudaStream_t)stream);
   if (rc != 0) {
@@ -211,6 +213,14 @@ void tgcn_graph_destroy(tgcn_graph_t* g) {
 }
 
 int64_t tgcn_graph_num_segments(const tgcn_graph_t* g) { return g ? g->n_segments : -1; }
+
+int tgcn_graph_set_hot_rows(tgcn_graph_t* g, int64_t hot_rows) {
+  TGCN_REQUIRE(g != nullptr, "graph is NULL");
+  TGCN_REQUIRE(hot_rows >= -1 && hot_rows <= g->n_rows, "hot_rows out of range");
+  g->l2_hints = hot_rows >= 0;
+  g->hot_rows = hot_rows < 0 ? 0 : (int)hot_rows;
+  return 0;
+}
 
 int tgcn_graph_set_mask_col_offset(tgcn_graph_t* g, int64_t col_offset) {
   TGCN_REQUIRE(g != nullptr, "graph is NULL");

@@ -8,6 +8,8 @@
 // per step and kBatch non-zeros are in flight per warp.  Rows longer than kSplitThreshold are cut
 // into kSegmentLen-nnz segments handled by separate warps that write partial sums; a tiny second
 // kernel adds the partials in fixed order, so results are deterministic run to run.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tgcn {
@@ -35,6 +37,8 @@ struct SpmmArgs {
   const float* x_user;  // gather source: c < x_split ? x_user + c·d : x_item + (c - x_split)·d
   const float* x_item;
   int x_split;
+  int hot_rows;  // rows [0, hot_rows) gather from a table worth keeping in L2 (evict_last); -1 = no cache hints
+  int hint_mode;  // bit 0: evict_last on hot gathers, bit 1: evict_first on cold gathers, bit 2: evict_first on col/val
   int n_rows;
   int d;
   const Segment* segments;
@@ -160,6 +164,44 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
   }
 }
 
+// L2 cache-policy hints — EXPERIMENTAL, off unless TGCN_L2_MODE is set (bit 0: evict_last on the item-table gathers
+// of user rows, bit 1: evict_first on the user-table gathers, bit 2: evict_first on the col/val stream).  Idea: at the
+// 200M-edge config the tables exceed the 126 MB L2 (ncu: 11 % L2 hit rate, 184 GB DRAM traffic per layer at 82 % of
+// DRAM peak) and the item table is small and popularity-skewed.  Measured on B200: every mode was 3-8 % slower than
+// plain ld.global.nc (116.3 ms/step without, 120.5-125.8 ms with), so the default stays hint-free.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ldg_hint_i32(const int* ptr, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_hint_f32(const float* ptr, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+
 // ---- main kernel (exact widths d = 4·LPN·VPL) -----------------------------------------------------------
 // One GROUP of LPN lanes per row (two rows per warp at d = 64, four at d = 32, one at d >= 128): each lane owns
 // VPL float4 columns of the output row and walks the row's non-zeros itself, kUnroll at a time, so there are
@@ -171,7 +213,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
 constexpr int kUnroll = 4;
 constexpr int kGroupThreads = 128;
 
-template <int LPN, int VPL>
+template <int LPN, int VPL, bool HINT>
 __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArgs a) {
   constexpr int D = 4 * LPN * VPL;
   const int tid = blockIdx.x * kGroupThreads + threadIdx.x;
@@ -198,14 +240,26 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
 #pragma unroll
   for (int w = 0; w < VPL; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool masked = a.keep != nullptr;
+  uint64_t pol_stream = 0, pol_x = 0;
+  if (HINT) {
+    const uint64_t normal = l2_policy_evict_normal();
+    pol_stream = (a.hint_mode & 4) ? l2_policy_evict_first() : normal;
+    pol_x = row < a.hot_rows ? ((a.hint_mode & 1) ? l2_policy_evict_last() : normal)
+                             : ((a.hint_mode & 2) ? l2_policy_evict_first() : normal);
+  }
   for (int p = begin; p < end; p += kUnroll) {
     int c[kUnroll];
     float v[kUnroll];
 #pragma unroll
     for (int i = 0; i < kUnroll; ++i) {
       const bool ok = p + i < end;
-      c[i] = ok ? __ldg(a.col + p + i) : -1;
-      v[i] = ok ? __ldg(a.val + p + i) : 0.f;
+      if (HINT) {
+        c[i] = ok ? ldg_hint_i32(a.col + p + i, pol_stream) : -1;
+        v[i] = ok ? ldg_hint_f32(a.val + p + i, pol_stream) : 0.f;
+      } else {
+        c[i] = ok ? __ldg(a.col + p + i) : -1;
+        v[i] = ok ? __ldg(a.val + p + i) : 0.f;
+      }
     }
     if (masked) {
 #pragma unroll
@@ -222,7 +276,9 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     for (int i = 0; i < kUnroll; ++i)
 #pragma unroll
       for (int w = 0; w < VPL; ++w)
-        x[i][w] = c[i] >= 0 ? ldg4(xb + (size_t)c[i] * D + w * (LPN * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[i][w] = c[i] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                  : HINT   ? ldg4_hint(xb + (size_t)c[i] * D + w * (LPN * 4), pol_x)
+                           : ldg4(xb + (size_t)c[i] * D + w * (LPN * 4));
 #pragma unroll
     for (int i = 0; i < kUnroll; ++i)
 #pragma unroll
@@ -277,7 +333,8 @@ template <int LPN, int VPL>
 static void launch_group(const SpmmArgs& a, cudaStream_t s) {
   const int64_t units = (int64_t)a.n_segments + a.n_rows;
   const int64_t blocks = (units * LPN + kGroupThreads - 1) / kGroupThreads;
-  spmm_group_kernel<LPN, VPL><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
+  if (a.hot_rows >= 0) spmm_group_kernel<LPN, VPL, true><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
+  else spmm_group_kernel<LPN, VPL, false><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
 }
 
 static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
@@ -336,6 +393,12 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.ep.divisor = 1.f;
   a.ep.accumulate = 0;
   a.x_split = g->is_block ? 0x7fffffff : (int)g->n_users;
+  // cache hints only pay when the gathered tables exceed L2 (~126 MB); hot_rows < 0 disables them
+  {
+    const char* m = getenv("TGCN_L2_MODE");
+    a.hint_mode = m ? atoi(m) : 0;  // off by default: measured 3-8 % SLOWER at the 200M-edge config (profiles/r01/README.md)
+  }
+  a.hot_rows = (g->l2_hints && a.hint_mode != 0 && (int64_t)(g->n_users + g->n_items) * d * 4 > (96ll << 20)) ? g->hot_rows : -1;
 }
 
 }  // namespace tgcn

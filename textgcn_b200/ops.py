@@ -115,6 +115,10 @@ class Graph:
             self._ws["buf"] = ws
         return ws
 
+    def set_hot_rows(self, n: int) -> None:
+        """Rows [0, n) gather from the small table to keep in L2 (evict_last hints); -1 disables cache hints."""
+        check(self.lib.tgcn_graph_set_hot_rows(self.handle, int(n)))
+
     def set_mask_col_offset(self, off: int) -> None:
         check(self.lib.tgcn_graph_set_mask_col_offset(self.handle, int(off)))
 

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the adv_sampling / LTR legs (BASELINE.json configs[2], [3])")
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--no-l2-hints", action="store_true", help="disable the L2 cache-policy hints of the SpMM (A/B comparison)")
     ap.add_argument("--mg-scheme", default="bipartite", choices=["bipartite", "rowblock"],
@@ -176,6 +177,63 @@ def train_leg(w, graph, dev, flush, torch, batch=2048, steps=10, warmup=3):
     return {"ms_per_step": ms, "batch": batch, "dropout": params.dropout, "steps_per_s": 1e3 / ms,
             "includes": "device dropout draw, L-layer propagate, fused BPR(SELU)+L2 kernel, Horner backward (L transposed SpMM), "
                         "fused Adam over both tables"}
+
+
+def extras_leg(w, graph, dev, flush, torch, batch=2048):
+    """BASELINE.json configs[2] (adv_sampling step: device candidate + positive sampling, hardest-of-1000 selection, BPR on
+    up to B·5·k triples, backward, fused Adam) and configs[3] (LTR ranking with random 768-d text tables)."""
+    import logging
+    from textgcn_b200.models import AdvSamplModel, LTRLinearWPop, make_params
+    from textgcn_b200.optim import FusedAdam
+    from textgcn_b200.sampler import AdvEpochSampler
+
+    class DS:
+        pass
+
+    ds = DS()
+    ds.n_users, ds.n_items, ds.graph, ds.norm_matrix = w["nu"], w["ni"], graph, None
+    ds.test_users, ds.true_test_lil = [0], [[0]]
+    log = logging.getLogger("bench")
+    out = {}
+    params = make_params(emb_size=w["d"], n_layers=w["L"], k=[20], batch_size=batch, fused_adam=True, dropout_rng="device",
+                         positive_sampler="device", device=dev, logger=log)
+    model = AdvSamplModel(params, ds)
+    opt = FusedAdam(model.parameters(), lr=params.lr)
+    smp = AdvEpochSampler(graph, batch_size=batch, seed=0)
+    users = torch.arange(batch, dtype=torch.int32, device=dev)
+    model.train()
+    model.training = True
+    n_triples = []
+
+    def adv_step():
+        data = smp.sample(users, 1234)
+        opt.zero_grad(set_to_none=False)
+        triples = model.select_triples(data)
+        n_triples.append(triples.shape[0])
+        loss = super(AdvSamplModel, model).get_loss(triples)
+        loss.backward()
+        opt.step()
+
+    t = timed_steps(adv_step, 5, 2, flush, torch)
+    out["adv_sampling"] = {"ms_per_step": sum(t) / len(t), "batch_users": batch, "candidates": smp.n_cand, "k": 20,
+                           "triples_per_step": n_triples[-1],
+                           "includes": "candidate + positive sampling kernels, propagate, adv_select_kernel, second propagate + fused BPR, "
+                                       "Horner backward, fused Adam"}
+    del model, opt
+    D = 768
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for name_, shape in (("items_as_avg_reviews", (w["ni"], D)), ("items_as_desc", (w["ni"], D)), ("users_as_avg_reviews", (w["nu"], D)),
+                         ("users_as_avg_desc", (w["nu"], D))):
+        setattr(ds, name_, torch.randn(*shape, generator=gen, device=dev))
+    ds.popularity_users = torch.rand(w["nu"], 1, generator=gen, device=dev)
+    ds.popularity_items = torch.rand(w["ni"], 1, generator=gen, device=dev)
+    ltr = LTRLinearWPop(make_params(emb_size=w["d"], n_layers=w["L"], k=[20], device=dev, logger=log), ds)
+    n_eval = 8192
+    t = timed_steps(lambda: ltr.predict_device(torch.arange(n_eval, dtype=torch.int32, device=dev)), 2, 1, flush, torch)
+    ms = sum(t) / len(t)
+    out["ltr_pop"] = {"users_per_s": n_eval / (ms * 1e-3), "ms": ms, "n_users_ranked": n_eval, "text_dim": D, "contraction_width": w["d"] + 2 * D,
+                      "includes": "propagate, ltr_pack_items/users, eval_topk_simt_kernel (K = d + 2D, fp32 FMA) with per-user/item bias, merge"}
+    return out
 
 
 def cpu_baseline(w, topk, n_predict=2048):
@@ -502,6 +560,12 @@ def main():
             extra["train"] = train_leg(w, graph, dev, flush, torch)
         except Exception as exc:
             extra["train"] = {"error": str(exc)[:300]}
+
+    if world == 1 and not args.no_extras and name != "c5":
+        try:
+            extra["configs"] = extras_leg(w, graph, dev, flush, torch)
+        except Exception as exc:
+            extra["configs"] = {"error": str(exc)[:300]}
 
     # ---- same workload on ONE GPU, measured by rank 0 in the same run (for honest strong-scaling ratios) ----
     if world > 1 and rank == 0:

@@ -189,6 +189,16 @@ int tgcn_ltr_pack_users(int64_t n_rank, const int32_t* d_users, int64_t d, int64
 int tgcn_sample_bpr_batch(const tgcn_graph_t* g, int64_t batch, int32_t n_neg, const int32_t* d_users, uint64_t seed,
                           int32_t max_tries, int64_t* d_out, int32_t* d_fail_count, tgcn_stream_t stream);
 
+/* a14 / n1  AdvSamplDataset.__getitem__ (advanced_sampling.py:21-22): row b of d_out (batch, 1 + n_cand) int64 is
+ * [d_users[b], n_cand distinct uniform item ids] — the head of a keyed random permutation of the items. */
+int tgcn_sample_candidates(int64_t n_items, int64_t batch, int32_t n_cand, const int32_t* d_users, uint64_t seed,
+                           int64_t* d_out, tgcn_stream_t stream);
+
+/* advanced_sampling.py:63-64: min(n_pos, deg(u)) distinct random positives of every batch user into d_out
+ * (batch, n_pos) int64, -1 padded — the device counterpart of random.sample(positives, 5). */
+int tgcn_sample_positives(const tgcn_graph_t* g, int64_t batch, int32_t n_pos, const int32_t* d_users, uint64_t seed,
+                          int64_t* d_out, tgcn_stream_t stream);
+
 /* n3 (next row)  dense Adam step over one table, torch.optim.Adam defaults (base_model.py:111, :126):
  * p, m, v updated in place from g; step is the 1-based step count. */
 int tgcn_adam_step(int64_t n, float* d_p, const float* d_g, float* d_m, float* d_v, float lr, float beta1,

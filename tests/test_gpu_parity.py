@@ -531,3 +531,40 @@ def test_gpu_sampler_properties_and_fit(ops):
     model.training = False
     model._loss_values = {"bpr": 0.0, "reg": 0.0}
     assert float(model.get_loss(batch)) < before
+
+
+def test_adv_device_samplers_and_fit(ops):
+    """a14 / n1: candidate rows are [user, distinct uniform items]; device positives are distinct members of the user's
+    train list; AdvSamplModel.fit() runs end to end on device-generated batches."""
+    from textgcn_b200.models import AdvSamplModel
+    from textgcn_b200.sampler import AdvEpochSampler
+    g = load_golden("small_adv")
+    gr = _graph(ops, g)
+    tl = golden_lists(g)
+    smp = AdvEpochSampler(gr, batch_size=32, seed=3)
+    rows = torch.cat(list(smp)).cpu().numpy()
+    assert rows.shape == (smp.rows, 1 + gr.n_items)                         # 70 items < 1000: every item, permuted
+    assert np.array_equal(np.sort(rows[:, 1:], axis=1), np.tile(np.arange(gr.n_items), (len(rows), 1)))
+    assert len({tuple(r) for r in rows[:, 1:].tolist()}) > len(rows) // 2      # rows get different permutations
+    # larger item set: 1000 distinct candidates, roughly uniform
+    tu, ti = O.synthetic_interactions(500, 5000, 20000, seed=2)
+    row, col, val = O.norm_adj_coo(tu, ti, 500, 5000)
+    big = ops.Graph.from_norm_matrix(O.sparse_tensor(row, col, val, 5500).to(DEV), 500, 5000)
+    cands = torch.cat(list(AdvEpochSampler(big, batch_size=256, seed=1))).cpu().numpy()[:, 1:]
+    assert cands.shape[1] == 1000 and cands.min() >= 0 and cands.max() < 5000
+    assert all(len(np.unique(r)) == 1000 for r in cands[:200])
+    freq = np.bincount(cands.ravel(), minlength=5000) / cands.shape[0]
+    assert abs(freq.mean() - 0.2) < 1e-9 and freq.min() > 0.1 and freq.max() < 0.3
+    # device positives
+    model = AdvSamplModel(params_from_golden(g, epochs=2, evaluate_every=2, positive_sampler="device", dropout_rng="device", lr=5e-3),
+                          StubDataset(g, DEV))
+    load_weights(model, g)
+    users = ops.as_index(np.arange(gr.n_users), DEV)
+    pos = model._sample_positives_device(users).cpu().numpy()
+    for u, prow in enumerate(pos):
+        got = prow[prow >= 0]
+        assert len(got) == min(5, len(tl[u])) and len(set(got)) == len(got) and np.isin(got, tl[u]).all()
+    model.fit(AdvEpochSampler(gr, batch_size=64, seed=5))
+    model.training = False
+    model._loss_values = {"bpr": 0.0, "reg": 0.0}
+    assert np.isfinite(float(model.get_loss(torch.from_numpy(g["data"]))))

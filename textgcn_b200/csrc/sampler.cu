@@ -61,9 +61,88 @@ __global__ void __launch_bounds__(256) sample_bpr_kernel(const SampleArgs a) {
   }
 }
 
+// a14  AdvSamplDataset.__getitem__ (advanced_sampling.py:21-22): n_cand DISTINCT uniform items per batch row.
+// Distinctness without a set: position q of row b maps through a keyed 4-round Feistel permutation of [0, 2^bits)
+// with cycle walking back into [0, n_items), i.e. the first n_cand entries of a random permutation of the items.
+__device__ __forceinline__ uint32_t feistel_perm(uint32_t x, int half_bits, unsigned long long key, uint32_t n) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  do {
+    uint32_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {
+      const uint32_t f = mix32(key + ((unsigned long long)round << 32) + r) & mask;
+      const uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (l << half_bits) | r;
+  } while (x >= n);
+  return x;
+}
+
+__global__ void __launch_bounds__(256) sample_candidates_kernel(int n_items, int half_bits, int batch, int n_cand,
+                                                                unsigned long long seed, const int* __restrict__ users,
+                                                                long long* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)batch * n_cand) return;
+  const int b = (int)(t / n_cand), q = (int)(t % n_cand);
+  const unsigned long long key = seed ^ ((unsigned long long)(b + 1) * 0x9E3779B97F4A7C15ULL);
+  long long* row = out + (size_t)b * (1 + n_cand);
+  if (q == 0) row[0] = __ldg(users + b);
+  row[1 + q] = feistel_perm((uint32_t)q, half_bits, key, (uint32_t)n_items);
+}
+
+// advanced_sampling.py:63-64: min(n_pos, deg) distinct random positives per row (head of a keyed permutation of the
+// user's train list), -1 padded.
+__global__ void __launch_bounds__(256) sample_positives_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_users,
+                                                               int batch, int n_pos, unsigned long long seed,
+                                                               const int* __restrict__ users, long long* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * n_pos) return;
+  const int b = t / n_pos, q = t % n_pos;
+  const int u = __ldg(users + b);
+  const int lo = __ldg(rowptr + u), deg = __ldg(rowptr + u + 1) - lo;
+  long long v = -1;
+  if (q < deg) {
+    int bits = 2;
+    while ((1 << bits) < deg) ++bits;
+    if (bits & 1) ++bits;
+    const unsigned long long key = seed ^ ((unsigned long long)(b + 1) * 0xD6E8FEB86659FD93ULL);
+    v = __ldg(col + lo + (int)feistel_perm((uint32_t)q, bits / 2, key, (uint32_t)deg)) - n_users;
+  }
+  out[(size_t)b * n_pos + q] = v;
+}
+
 }  // namespace tgcn
 
 using namespace tgcn;
+
+extern "C" int tgcn_sample_positives(const tgcn_graph_t* g, int64_t batch, int32_t n_pos, const int32_t* d_users, uint64_t seed,
+                                     int64_t* d_out, tgcn_stream_t stream) {
+  TGCN_REQUIRE(g != nullptr && !g->is_block, "sampler needs a whole-graph handle");
+  TGCN_REQUIRE(batch > 0 && n_pos > 0 && batch * (int64_t)n_pos < (1ll << 31), "bad sizes");
+  TGCN_REQUIRE(d_users && d_out, "NULL argument");
+  const int total = (int)(batch * n_pos);
+  sample_positives_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g->rowptr, g->col, (int)g->n_users, (int)batch, n_pos,
+                                                                                (unsigned long long)seed, d_users, (long long*)d_out);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int tgcn_sample_candidates(int64_t n_items, int64_t batch, int32_t n_cand, const int32_t* d_users, uint64_t seed,
+                                      int64_t* d_out, tgcn_stream_t stream) {
+  TGCN_REQUIRE(n_items > 0 && n_items < (1ll << 31) && batch > 0 && n_cand > 0 && n_cand <= n_items, "bad sizes: n_items=%lld n_cand=%d",
+               (long long)n_items, n_cand);
+  TGCN_REQUIRE(d_users && d_out, "NULL argument");
+  int bits = 2;
+  while ((1ll << bits) < n_items) ++bits;
+  if (bits & 1) ++bits;  // balanced Feistel halves
+  const long long total = batch * (long long)n_cand;
+  sample_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)n_items, bits / 2, (int)batch, n_cand,
+                                                                                           (unsigned long long)seed, d_users, (long long*)d_out);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int tgcn_sample_bpr_batch(const tgcn_graph_t* g, int64_t batch, int32_t n_neg, const int32_t* d_users, uint64_t seed,
                                      int32_t max_tries, int64_t* d_out, int32_t* d_fail_count, tgcn_stream_t stream) {

@@ -404,8 +404,21 @@ class BaseModel(B200HotPath, nn.Module):
 class B200AdvSampl:
     """Overrides of AdvSamplModel: ranking + positive removal + top max(k) as one kernel per batch."""
 
+    positive_sampler = "host"  # "host": Python random.sample like the reference; "device": keyed permutation kernel
+
     def score_pairwise_adv(self, users_emb, items_emb):
         raise TgcnError("score_pairwise_adv is fused into get_loss(): the (B, 1000, d) gather is never materialised")
+
+    def _sample_positives_device(self, users: torch.Tensor) -> torch.Tensor:
+        """Device counterpart of ``_sample_positives`` (advanced_sampling.py:63-64), (B, pos_samples) int64, -1 padded."""
+        g = self.graph
+        out = torch.empty((users.numel(), self.pos_samples), dtype=torch.int64, device=g.device)
+        self.__dict__["_b200_pos_calls"] = self.__dict__.get("_b200_pos_calls", 0) + 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + self.__dict__["_b200_pos_calls"] * 0x85EBCA77) & (2 ** 63 - 1)
+        with torch.cuda.device(g.device):
+            ops.check(g.lib.tgcn_sample_positives(g.handle, users.numel(), self.pos_samples, users.data_ptr(), seed,
+                                                  out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return out
 
     def _sample_positives(self, users: Sequence[int]) -> torch.Tensor:
         """advanced_sampling.py:63-64: <= pos_samples random positives per user from Python's RNG, -1 padded."""
@@ -429,7 +442,8 @@ class B200AdvSampl:
                                      self.n_layers, self._single(), self._draw_keep_mask(), float(self.dropout))
             negs, counts, _ = ops.adv_select(self.graph, out, users, cands, max(self.k))
         if sampled_pos is None:
-            sampled_pos = self._sample_positives(users64.tolist())
+            sampled_pos = (self._sample_positives_device(users) if self.positive_sampler == "device"
+                           else self._sample_positives(users64.tolist()))
         sampled_pos = sampled_pos.to(dev)
         valid = (sampled_pos >= 0)[:, :, None] & (negs >= 0)[:, None, :]
         b, p, n = torch.nonzero(valid, as_tuple=True)  # row-major: batch, then positive, then negative
@@ -441,10 +455,14 @@ class B200AdvSampl:
 
 
 class AdvSamplModel(B200AdvSampl, BaseModel):
+    def _copy_params(self, params):
+        super()._copy_params(params)
+        self.positive_sampler = getattr(params, "positive_sampler", "host")
+
     def _copy_dataset_params(self, dataset):
         super()._copy_dataset_params(dataset)
-        self.positive_lists = dataset.positive_lists
-        self.pos_samples = dataset.pos_samples
+        self.positive_lists = getattr(dataset, "positive_lists", None)
+        self.pos_samples = getattr(dataset, "pos_samples", 5)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -46,3 +46,23 @@ class BprEpochSampler:
         self.epoch += 1
         for i, s in enumerate(range(0, self.rows, self.batch_size)):
             yield self.sample(users[s:s + self.batch_size].contiguous(), base + i * 0xC2B2AE3D)
+
+
+class AdvEpochSampler(BprEpochSampler):
+    """Batches for AdvSamplModel: rows [user, 1000 distinct random candidate items] (advanced_sampling.py:10-22),
+    generated on the device — the reference spends 7.3 s of an 8.7 s step in ``random.sample`` here."""
+
+    max_neg_samples = 1000
+
+    def __init__(self, graph: ops.Graph, batch_size: int = 2048, seed: int = 0):
+        super().__init__(graph, batch_size, 1, seed)
+        self.n_cand = min(graph.n_items, self.max_neg_samples)
+
+    def sample(self, users: torch.Tensor, seed: int) -> torch.Tensor:
+        g = self.graph
+        users = ops._chk(users, torch.int32, "users", 1, align=4)
+        out = torch.empty((users.numel(), 1 + self.n_cand), dtype=torch.int64, device=g.device)
+        with torch.cuda.device(g.device):
+            check(g.lib.tgcn_sample_candidates(g.n_items, users.numel(), self.n_cand, users.data_ptr(), seed & (2 ** 64 - 1),
+                                               out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return out

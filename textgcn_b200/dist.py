@@ -19,6 +19,7 @@ logic is unit-tested with world_size-2 gloo on CPU; the defaults are the CUDA ke
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -186,24 +187,26 @@ class BipartitePropagator:
         Writes this rank's rows of users_emb and the whole items_emb."""
         L = self.n_layers
         ws = self.part.world_size
+        probe = os.environ.get("TGCN_MG_PROBE", "")  # "nocomm" / "nocompute": timing probes for the overlap analysis only
+        spmm = (lambda *a: None) if probe == "nocompute" else self.spmm_fn
 
         def reduce_async(t):
-            return dist.all_reduce(t, group=self.group, async_op=True) if ws > 1 else None
+            return dist.all_reduce(t, group=self.group, async_op=True) if (ws > 1 and probe != "nocomm") else None
 
         # Software pipeline: the all-reduce of layer l's item table (AR_l) only feeds the USER rows of layer l+1, so it
         # runs behind two local SpMMs: A_l (user rows of layer l, needs AR_{l-1}) and B_{l+1} (item partials of layer
         # l+1, needs A_l's output).  Compute per hop = A + B back to back; the collective is hidden behind it.
-        self.spmm_fn(self.ig, e0_user_local, self.ibufs[0], [], 1.0)       # B_1: partial item rows of layer 1
+        spmm(self.ig, e0_user_local, self.ibufs[0], [], 1.0)               # B_1: partial item rows of layer 1
         work = reduce_async(self.ibufs[0])
         cur_i = e0_item
         for layer in range(1, L + 1):
             last = layer == L
             if last:                                                        # A_l: user rows of layer l (local)
                 adds = [] if single else [e0_user_local] + self.ubufs
-                self.spmm_fn(self.ug, cur_i, out_user_local, adds, 1.0 if single else float(L + 1))
+                spmm(self.ug, cur_i, out_user_local, adds, 1.0 if single else float(L + 1))
             else:
-                self.spmm_fn(self.ug, cur_i, self.ubufs[layer - 1], [], 1.0)
-                self.spmm_fn(self.ig, self.ubufs[layer - 1], self.ibufs[layer], [], 1.0)   # B_{l+1}
+                spmm(self.ug, cur_i, self.ubufs[layer - 1], [], 1.0)
+                spmm(self.ig, self.ubufs[layer - 1], self.ibufs[layer], [], 1.0)   # B_{l+1}
             if work is not None:
                 work.wait()                                                 # item table of layer l is complete
             cur_i = self.ibufs[layer - 1]

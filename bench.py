@@ -342,6 +342,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL logs (e.g. its version banner at NCCL_DEBUG=VERSION) go to stdout by default: keep stdout to the ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     name = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c5")
     w = build_workload(name, dev)

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the adv_sampling / LTR legs (BASELINE.json configs[2], [3])")
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--no-l2-hints", action="store_true", help="disable the L2 cache-policy hints of the SpMM (A/B comparison)")
+    ap.add_argument("--ar-chunks", type=int, default=1, help="bipartite scheme: split the item-table all-reduce into this many chunks")
     ap.add_argument("--mg-scheme", default="bipartite", choices=["bipartite", "rowblock"],
                     help="multi-GPU propagation: users partitioned + item-table all-reduce, or row blocks + all-gather")
     return ap.parse_args()
@@ -368,7 +369,7 @@ def main():
 
         sampler.start()
         times = timed_steps(step, args.steps, args.warmup, flush, torch)
-        launches_per_step = L * (2 if graph.n_segments > 0 else 1)
+        launches_per_step = L
         parallelism = "single GPU"
         scaling = "weak"
     elif args.mg_scheme == "rowblock":
@@ -387,7 +388,7 @@ def main():
         sampler.start()
         times = timed_steps(step, args.steps, args.warmup, flush, torch)
         dist.barrier()
-        launches_per_step = L * (2 if lgraph.n_segments > 0 else 1)
+        launches_per_step = L
         parallelism = f"row-block x{world}, NCCL all-gather of layer embeddings between hops"
         scaling = "strong"
         extra["comm_bytes_per_hop_per_rank"] = prop.comm_bytes_per_hop
@@ -399,7 +400,17 @@ def main():
         ugraph.set_mask_col_offset(0)
         ugraph.set_hot_rows(u1 - u0)  # every row of this block gathers from the replicated item table: keep it in L2
         igraph = ops.Graph(nu, ni, *part.item_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=nu, block=True)
-        prop = tdist.BipartitePropagator(part, rank, ugraph, igraph, d, L, dev)
+        chunks = None
+        if args.ar_chunks > 1:  # chunked item rows: each chunk's all-reduce starts as soon as its SpMM is enqueued
+            irp, icol, ival = igraph.rowptr, igraph.col, igraph.val
+            chunks = []
+            for c in range(args.ar_chunks):
+                r0, r1 = ni * c // args.ar_chunks, ni * (c + 1) // args.ar_chunks
+                lo, hi = int(irp[r0]), int(irp[r1])
+                h = ops.Graph(nu, ni, (irp[r0:r1 + 1] - irp[r0]).contiguous(), icol[lo:hi].contiguous(), ival[lo:hi].contiguous(),
+                              row_begin=nu + r0, block=True)
+                chunks.append((r0, r1, h))
+        prop = tdist.BipartitePropagator(part, rank, ugraph, igraph, d, L, dev, item_chunks=chunks)
         e0_u = w["uw"][u0:u1].contiguous()
         out_u = torch.empty((u1 - u0, d), dtype=torch.float32, device=dev)
         out_i = torch.empty((ni, d), dtype=torch.float32, device=dev)
@@ -411,7 +422,7 @@ def main():
         sampler.start()
         times = timed_steps(step, args.steps, args.warmup, flush, torch)
         dist.barrier()
-        launches_per_step = 2 * L * (2 if (ugraph.n_segments + igraph.n_segments) > 0 else 1) + 1
+        launches_per_step = 2 * L + 1 + (args.ar_chunks - 1) * L
         parallelism = f"users partitioned x{world} by nnz, item table replicated: NCCL all-reduce of (I, d) per hop overlapped with the user-row SpMM"
         scaling = "strong"
         extra["comm_bytes_per_hop_per_rank"] = prop.comm_bytes_per_hop

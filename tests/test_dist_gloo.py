@@ -107,6 +107,18 @@ def _worker(rank, world, port, case, ret):
         bprop.propagate(e0[u0:u1].contiguous(), e0[nu:].contiguous(), out_u, out_i, single=bool(g["single"]))
         assert np.abs(out_u.numpy() - g["rep_user"][u0:u1]).max() / np.abs(g["rep_user"]).max() < 1e-6
         assert np.abs(out_i.numpy() - g["rep_item"]).max() / np.abs(g["rep_item"]).max() < 1e-6
+        # same with the item rows (and their all-reduce) split into 3 chunks
+        irp, icol, ival = ig
+        chunks = []
+        for c in range(3):
+            r0, r1 = ni * c // 3, ni * (c + 1) // 3
+            lo, hi = int(irp[r0]), int(irp[r1])
+            chunks.append((r0, r1, ((irp[r0:r1 + 1] - irp[r0]).contiguous(), icol[lo:hi].contiguous(), ival[lo:hi].contiguous())))
+        cprop = tdist.BipartitePropagator(bp, rank, ug, ig, d, L, "cpu", spmm_fn=_cpu_spmm, item_chunks=chunks,
+                                          mean_fn=lambda adds, out, div: out.copy_(sum(adds[1:], adds[0]) / div))
+        out_u2, out_i2 = torch.empty_like(out_u), torch.empty_like(out_i)
+        cprop.propagate(e0[u0:u1].contiguous(), e0[nu:].contiguous(), out_u2, out_i2, single=bool(g["single"]))
+        assert torch.equal(out_u2, out_u) and torch.equal(out_i2, out_i)
         # item-sharded eval with cross-rank merge
         k = int(max(g["ks"]))
         tl = golden_lists(g)

@@ -32,11 +32,13 @@ void set_error(const char* fmt, ...);
 constexpr int kSplitThreshold = 128;  // rows longer than this are cut into segments
 constexpr int kSegmentLen = 64;       // nnz per segment of a long row
 
-struct Segment {  // one warp's share of a long row
+struct Segment {  // one warp's (or lane group's) share of a long row
   int row;        // local row index
   int begin;      // nnz range
   int end;
   int slot;       // index into the partial-sum scratch
+  int split;      // index of the row in the split-row table
+  int pad[3];
 };
 struct SplitRow {
   int row;
@@ -61,6 +63,7 @@ struct tgcn_graph {
   int n_segments;
   tgcn::SplitRow* split_rows;
   int n_split_rows;
+  int* split_counters;  // arrivals per split row (self-resetting; one launch in flight per handle)
   int max_degree;
   int mask_col_off;  // eval masks: entry value = mask_col_off + item id (n_users unless overridden)
   int l2_hints;   // allow L2 cache-policy hints on large tables

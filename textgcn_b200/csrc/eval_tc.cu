@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -310,10 +311,11 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + g * 32, v);
         const int nbase = n0 + g * 32;
         // hit mask: one FSETP + one predicated OR per score against the row's current k-th best
-        uint32_t hits = 0;
+        uint32_t h4[4] = {0u, 0u, 0u, 0u};  // four independent OR chains instead of one 32-long dependency chain
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (__uint_as_float(v[j]) > thr) hits |= 1u << j;
+          if (__uint_as_float(v[j]) > thr) h4[j & 3] |= 1u << j;
+        uint32_t hits = (h4[0] | h4[1]) | (h4[2] | h4[3]);
         const int rem = a.n_range - nbase;  // columns past the item range hold zero-filled rows
         if (rem < 32) hits &= rem > 0 ? (1u << rem) - 1u : 0u;
         if (!valid) hits = 0;
@@ -495,8 +497,10 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
     TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     eval_topk_tc_kernel<BN_, KL_, EW_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                               \
   } while (0)
+  static const int ew20 = getenv("TGCN_TC_EW") ? atoi(getenv("TGCN_TC_EW")) : 2;  // tuning knob (2 or 4 warps per lane quarter)
   if (bn == 256) {
-    if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2);
+    if (k <= 20 && ew20 == 4) TGCN_TC_LAUNCH(256, 20, 4);
+    else if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2);
     else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2);
     else TGCN_TC_LAUNCH(256, 64, 1);
   } else {

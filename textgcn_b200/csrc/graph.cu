@@ -96,7 +96,7 @@ static int build_segments(tgcn_graph* g, cudaStream_t stream) {
       SplitRow sr{(int)r, (int)segs.size(), 0, 0};
       for (int b = rowptr[r]; b < rowptr[r + 1]; b += kSegmentLen) {
         int e = b + kSegmentLen < rowptr[r + 1] ? b + kSegmentLen : rowptr[r + 1];
-        segs.push_back(Segment{(int)r, b, e, (int)segs.size()});
+        segs.push_back(Segment{(int)r, b, e, (int)segs.size(), (int)splits.size(), {0, 0, 0}});
         sr.n_parts++;
       }
       splits.push_back(sr);
@@ -108,6 +108,8 @@ static int build_segments(tgcn_graph* g, cudaStream_t stream) {
   if (!segs.empty()) {
     TGCN_CHECK_CUDA(cudaMalloc(&g->segments, sizeof(Segment) * segs.size()));
     TGCN_CHECK_CUDA(cudaMalloc(&g->split_rows, sizeof(SplitRow) * splits.size()));
+    TGCN_CHECK_CUDA(cudaMalloc(&g->split_counters, sizeof(int) * splits.size()));
+    TGCN_CHECK_CUDA(cudaMemsetAsync(g->split_counters, 0, sizeof(int) * splits.size(), stream));
     TGCN_CHECK_CUDA(cudaMemcpyAsync(g->segments, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, stream));
     TGCN_CHECK_CUDA(cudaMemcpyAsync(g->split_rows, splits.data(), sizeof(SplitRow) * splits.size(), cudaMemcpyHostToDevice, stream));
     TGCN_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -149,6 +151,7 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->tperm = nullptr;
   g->segments = nullptr;
   g->split_rows = nullptr;
+  g->split_counters = nullptr;
   g->n_segments = g->n_split_rows = 0;
   g->bipartite = 0;
   g->mask_col_off = (int)n_users;
@@ -209,6 +212,7 @@ void tgcn_graph_destroy(tgcn_graph_t* g) {
   if (g->tperm) cudaFree(g->tperm);
   if (g->segments) cudaFree(g->segments);
   if (g->split_rows) cudaFree(g->split_rows);
+  if (g->split_counters) cudaFree(g->split_counters);
   delete g;
 }
 

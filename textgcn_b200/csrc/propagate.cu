@@ -6,8 +6,8 @@
 // Work decomposition: one warp per row; the warp's lanes are split into G = 32/LPN groups of LPN
 // lanes, each lane owning VPL float4 of the d-wide row (d = 4·LPN·VPL), so G non-zeros are gathered
 // per step and kBatch non-zeros are in flight per warp.  Rows longer than kSplitThreshold are cut
-// into kSegmentLen-nnz segments handled by separate warps that write partial sums; a tiny second
-// kernel adds the partials in fixed order, so results are deterministic run to run.
+// into kSegmentLen-nnz segments handled by separate warps that write partial sums; the last segment
+// of a row to finish adds the partials in fixed order, so results are deterministic run to run.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -43,6 +43,8 @@ struct SpmmArgs {
   int d;
   const Segment* segments;
   int n_segments;
+  const SplitRow* split_rows;
+  int* split_counters;
   float* partial;  // (n_segments, d)
   float* y;        // (n_rows, d)
   Epilogue ep;
@@ -70,19 +72,42 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int row, int c
   *out = s;
 }
 
+// Long rows: every segment writes its partial sum, then signals; the LAST segment of a row to arrive adds the partials
+// in slot order (deterministic) and applies the epilogue, so no second kernel is needed.  `leader` is one lane of the
+// group, `mask` the group's lanes.  Pattern: store, __threadfence, atomic; last arriver fences and reads through L2.
+__device__ __forceinline__ bool segment_arrive_is_last(const SpmmArgs& a, int split, bool leader, unsigned mask, int leader_lane) {
+  __threadfence();
+  int old = 0;
+  const int n_parts = a.split_rows[split].n_parts;
+  if (leader) old = atomicAdd(a.split_counters + split, 1);
+  old = __shfl_sync(mask, old, leader_lane);
+  if (old != n_parts - 1) return false;
+  __threadfence();
+  if (leader) a.split_counters[split] = 0;  // re-arm for the next launch on this handle
+  return true;
+}
+__device__ __forceinline__ float4 sum_partials(const SpmmArgs& a, int split, int chunk) {
+  const SplitRow sr = a.split_rows[split];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int part = 0; part < sr.n_parts; ++part)
+    add4(acc, __ldcg(reinterpret_cast<const float4*>(a.partial + (size_t)(sr.first_slot + part) * a.d + chunk * 4)));
+  return acc;
+}
+
 template <int LPN, int VPL>
 __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
   constexpr int G = 32 / LPN;
   constexpr int U = (kBatch / G) > 0 ? (kBatch / G) : 1;
   const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  int row, begin, end, slot;
+  int row, begin, end, slot, split = -1;
   if (warp < a.n_segments) {
     const Segment s = a.segments[warp];
     row = s.row;
     begin = s.begin;
     end = s.end;
     slot = s.slot;
+    split = s.split;
   } else {
     row = warp - a.n_segments;
     if (row >= a.n_rows) return;
@@ -162,6 +187,16 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
     if (slot >= 0) *reinterpret_cast<float4*>(a.partial + (size_t)slot * a.d + chunk * 4) = acc[w];
     else epilogue_store(a, row, chunk, acc[w]);
   }
+  if (slot >= 0) {
+    const unsigned mask = LPN == 32 ? 0xffffffffu : ((1u << LPN) - 1u);
+    if (segment_arrive_is_last(a, split, sub == 0, mask, 0)) {
+#pragma unroll
+      for (int w = 0; w < VPL; ++w) {
+        const int chunk = sub + w * LPN;
+        if (chunk < d4) epilogue_store(a, row, chunk, sum_partials(a, split, chunk));
+      }
+    }
+  }
 }
 
 // L2 cache-policy hints — EXPERIMENTAL, off unless TGCN_L2_MODE is set (bit 0: evict_last on the item-table gathers
@@ -218,13 +253,14 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
   constexpr int D = 4 * LPN * VPL;
   const int tid = blockIdx.x * kGroupThreads + threadIdx.x;
   const int unit = tid / LPN, sub = tid % LPN;
-  int row, begin, end, slot;
+  int row, begin, end, slot, split = -1;
   if (unit < a.n_segments) {
     const Segment s = a.segments[unit];
     row = s.row;
     begin = s.begin;
     end = s.end;
     slot = s.slot;
+    split = s.split;
   } else {
     row = unit - a.n_segments;
     if (row >= a.n_rows) return;
@@ -290,20 +326,17 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     if (slot >= 0) *reinterpret_cast<float4*>(a.partial + (size_t)slot * D + chunk * 4) = acc[w];
     else epilogue_store(a, row, chunk, acc[w]);
   }
-}
-
-// One warp per long row: add its segment partials in order, then the epilogue.
-__global__ void __launch_bounds__(128) spmm_fixup_kernel(const SpmmArgs a, const SplitRow* __restrict__ rows, int n_split) {
-  const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_split) return;
-  const SplitRow sr = rows[warp];
-  const int d4 = a.d >> 2;
-  for (int chunk = lane; chunk < d4; chunk += 32) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int part = 0; part < sr.n_parts; ++part)
-      add4(acc, *reinterpret_cast<const float4*>(a.partial + (size_t)(sr.first_slot + part) * a.d + chunk * 4));
-    epilogue_store(a, sr.row, chunk, acc);
+  if (slot >= 0) {
+    const int lane = threadIdx.x & 31;
+    const int first = lane - sub;  // first lane of this group inside the warp
+    const unsigned mask = LPN == 32 ? 0xffffffffu : (((1u << LPN) - 1u) << first);
+    if (segment_arrive_is_last(a, split, sub == 0, mask, first)) {
+#pragma unroll
+      for (int w = 0; w < VPL; ++w) {
+        const int chunk = sub + w * LPN;
+        epilogue_store(a, row, chunk, sum_partials(a, split, chunk));
+      }
+    }
   }
 }
 
@@ -358,12 +391,6 @@ static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
   else if (d <= 512) spmm_rows_kernel<32, 4><<<(unsigned)blocks, threads, 0, s>>>(a);
   else TGCN_REQUIRE(false, "embedding width %d > 512 is not supported", d);
   TGCN_CHECK_LAUNCH();
-  if (g->n_split_rows > 0) {
-    const int fthreads = 128;
-    const int fblocks = (g->n_split_rows * 32 + fthreads - 1) / fthreads;
-    spmm_fixup_kernel<<<fblocks, fthreads, 0, s>>>(a, g->split_rows, g->n_split_rows);
-    TGCN_CHECK_LAUNCH();
-  }
   return 0;
 }
 
@@ -388,6 +415,8 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.d = (int)d;
   a.segments = g->segments;
   a.n_segments = g->n_segments;
+  a.split_rows = g->split_rows;
+  a.split_counters = g->split_counters;
   a.ep.n_add = 0;
   a.ep.add_split = g->is_block ? 0x7fffffff : (int)g->n_users;
   a.ep.divisor = 1.f;

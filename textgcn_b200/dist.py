@@ -172,8 +172,12 @@ class BipartitePropagator:
     """K-layer propagation with users partitioned and the item table all-reduced once per hop."""
 
     def __init__(self, part: BipartitePartition, rank: int, user_graph, item_graph, d: int, n_layers: int, device,
-                 group=None, spmm_fn: Callable = _default_spmm, mean_fn: Callable = _default_mean):
+                 group=None, spmm_fn: Callable = _default_spmm, mean_fn: Callable = _default_mean, item_chunks=None):
+        """``item_graph``: handle over all item rows restricted to the owned users.  ``item_chunks``: optional list of
+        (row_begin, row_end, handle) covering the item rows in order; each chunk's partial rows are all-reduced as soon as
+        that chunk's SpMM is enqueued, so the collective starts earlier and its exposed tail shrinks."""
         self.part, self.rank, self.ug, self.ig, self.d, self.n_layers = part, rank, user_graph, item_graph, d, n_layers
+        self.item_chunks = item_chunks or [(0, part.n_items, item_graph)]
         self.group, self.spmm_fn, self.mean_fn = group, spmm_fn, mean_fn
         u0, u1 = part.users(rank)
         self.n_local = u1 - u0
@@ -190,28 +194,33 @@ class BipartitePropagator:
         probe = os.environ.get("TGCN_MG_PROBE", "")  # "nocomm" / "nocompute": timing probes for the overlap analysis only
         spmm = (lambda *a: None) if probe == "nocompute" else self.spmm_fn
 
-        def reduce_async(t):
-            return dist.all_reduce(t, group=self.group, async_op=True) if (ws > 1 and probe != "nocomm") else None
+        def item_partials(src_u, dst):
+            """B: partial item rows over the owned users, chunk by chunk, each chunk's all-reduce launched right behind it."""
+            works = []
+            for r0, r1, handle in self.item_chunks:
+                spmm(handle, src_u, dst[r0:r1], [], 1.0)
+                if ws > 1 and probe != "nocomm":
+                    works.append(dist.all_reduce(dst[r0:r1], group=self.group, async_op=True))
+            return works
 
         # Software pipeline: the all-reduce of layer l's item table (AR_l) only feeds the USER rows of layer l+1, so it
         # runs behind two local SpMMs: A_l (user rows of layer l, needs AR_{l-1}) and B_{l+1} (item partials of layer
         # l+1, needs A_l's output).  Compute per hop = A + B back to back; the collective is hidden behind it.
-        spmm(self.ig, e0_user_local, self.ibufs[0], [], 1.0)               # B_1: partial item rows of layer 1
-        work = reduce_async(self.ibufs[0])
+        works = item_partials(e0_user_local, self.ibufs[0])                  # B_1 (+ AR_1)
         cur_i = e0_item
         for layer in range(1, L + 1):
             last = layer == L
+            nxt = []
             if last:                                                        # A_l: user rows of layer l (local)
                 adds = [] if single else [e0_user_local] + self.ubufs
                 spmm(self.ug, cur_i, out_user_local, adds, 1.0 if single else float(L + 1))
             else:
                 spmm(self.ug, cur_i, self.ubufs[layer - 1], [], 1.0)
-                spmm(self.ig, self.ubufs[layer - 1], self.ibufs[layer], [], 1.0)   # B_{l+1}
-            if work is not None:
-                work.wait()                                                 # item table of layer l is complete
+                nxt = item_partials(self.ubufs[layer - 1], self.ibufs[layer])   # B_{l+1}; AR_{l+1} queues behind AR_l
+            for wk in works:
+                wk.wait()                                                   # item table of layer l is complete
+            works = nxt
             cur_i = self.ibufs[layer - 1]
-            if not last:
-                work = reduce_async(self.ibufs[layer])
         if single:
             out_item.copy_(cur_i)
         else:

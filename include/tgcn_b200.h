@@ -189,6 +189,10 @@ int tgcn_ltr_pack_users(int64_t n_rank, const int32_t* d_users, int64_t d, int64
 int tgcn_sample_bpr_batch(const tgcn_graph_t* g, int64_t batch, int32_t n_neg, const int32_t* d_users, uint64_t seed,
                           int32_t max_tries, int64_t* d_out, int32_t* d_fail_count, tgcn_stream_t stream);
 
+/* n2 (next row)  the edge-dropout keep mask of base_model.py:82 drawn on the device: d_keep[p] = 1 with probability
+ * 1 - dropout (counter-based hash of (seed, p)), one byte per nnz, consumed by tgcn_propagate_fwd/_bwd/_spmm_ex. */
+int tgcn_dropout_mask(int64_t nnz, float dropout, uint64_t seed, uint8_t* d_keep, tgcn_stream_t stream);
+
 /* a14 / n1  AdvSamplDataset.__getitem__ (advanced_sampling.py:21-22): row b of d_out (batch, 1 + n_cand) int64 is
  * [d_users[b], n_cand distinct uniform item ids] — the head of a keyed random permutation of the items. */
 int tgcn_sample_candidates(int64_t n_items, int64_t batch, int32_t n_cand, const int32_t* d_users, uint64_t seed,

@@ -568,3 +568,22 @@ def test_adv_device_samplers_and_fit(ops):
     model.training = False
     model._loss_values = {"bpr": 0.0, "reg": 0.0}
     assert np.isfinite(float(model.get_loss(torch.from_numpy(g["data"]))))
+
+
+def test_device_dropout_mask_statistics(ops):
+    """n2: the device-drawn keep mask is Bernoulli(1 - p), reproducible from its seed, and differs between seeds."""
+    n = 1_000_003
+    for p in (0.0, 0.4, 0.9):
+        k1 = ops.dropout_mask(n, p, 123, DEV)
+        k2 = ops.dropout_mask(n, p, 123, DEV)
+        k3 = ops.dropout_mask(n, p, 124, DEV)
+        assert k1.dtype == torch.uint8 and set(torch.unique(k1).tolist()) <= {0, 1}
+        assert torch.equal(k1, k2)
+        frac = float(k1.float().mean())
+        assert abs(frac - (1 - p)) < 4 * np.sqrt(p * (1 - p) / n) + 1e-9
+        if 0 < p < 1:
+            assert not torch.equal(k1, k3)
+            agree = float((k1 == k3).float().mean())
+            assert abs(agree - (p * p + (1 - p) ** 2)) < 5e-3              # independent draws
+            lag = float((k1[1:] == k1[:-1]).float().mean())
+            assert abs(lag - (p * p + (1 - p) ** 2)) < 5e-3                # no serial correlation

@@ -51,6 +51,7 @@ SIGNATURES = {
     "tgcn_ltr_pack_users": (c_int32, [c_int64, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "tgcn_sample_bpr_batch": (c_int32, [_P, c_int64, c_int32, _P, ctypes.c_uint64, c_int32, _P, _P, _P]),
     "tgcn_sample_candidates": (c_int32, [c_int64, c_int64, c_int32, _P, ctypes.c_uint64, _P, _P]),
+    "tgcn_dropout_mask": (c_int32, [c_int64, c_float, ctypes.c_uint64, _P, _P]),
     "tgcn_sample_positives": (c_int32, [_P, c_int64, c_int32, _P, ctypes.c_uint64, _P, _P]),
     "tgcn_adam_step": (c_int32, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_int64, _P]),
 }

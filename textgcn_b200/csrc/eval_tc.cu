@@ -44,6 +44,10 @@ struct TcArgs {
   int mrow_begin, mcol_off;
   int* part_ids;
   float* part_scores;
+  int direct;    // single split: write the final table here (no merge pass), completing short lists when `finalize`
+  int finalize;
+  int* out_ids;
+  float* out_scores;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -351,7 +355,25 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         aphase ^= 1;
       }
     }
-    if (valid) {
+    if (valid && a.direct) {
+      int real = 0;  // the list is sorted, so sentinels (never-filled slots) come last
+#pragma unroll
+      for (int j = 0; j < KL; ++j) real += li[j] != INT_MAX ? 1 : 0;
+      const size_t o = (size_t)m * a.k;
+#pragma unroll
+      for (int j = 0; j < KL; ++j)
+        if (j < a.k) {
+          int id = li[j];
+          float s = ls[j];
+          if (a.finalize && j >= real) {  // fewer than k rankable items: complete with train items, lowest id first (G9)
+            const int tt = j - real;
+            id = tt < mhi - mlo ? __ldg(a.mcol + mlo + tt) - a.mcol_off : -1;
+            s = -INFINITY;
+          }
+          a.out_ids[o + j] = id;
+          a.out_scores[o + j] = s;
+        }
+    } else if (valid) {
       const size_t o = ((size_t)blockIdx.y * a.n_rank + m) * a.k;
 #pragma unroll
       for (int j = 0; j < KL; ++j)
@@ -452,8 +474,8 @@ void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_split
 
 int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
                  int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
-                 int64_t item_end, int32_t k, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
-                 float** part_scores_out, cudaStream_t s) {
+                 int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
+                 int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, cudaStream_t s) {
   int bn, n_stages;
   size_t smem;
   tc_plan((int)K, k, &bn, &n_stages, &smem);
@@ -491,6 +513,10 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   a.mcol_off = mcol_off;
   a.part_ids = part_ids;
   a.part_scores = part_scores;
+  a.direct = n_splits == 1;
+  a.finalize = finalize;
+  a.out_ids = d_out_ids;
+  a.out_scores = d_out_scores;
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
 #define TGCN_TC_LAUNCH(BN_, KL_, EW_)                                                                                        \
   do {                                                                                                                       \

@@ -336,8 +336,8 @@ bool eval_tc_eligible(int64_t K, int32_t k);
 int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, int n_splits);
 int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
                  int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K,
-                 int64_t item_begin, int64_t item_end, int32_t k, void* d_workspace, int64_t workspace_bytes, int* n_splits_out,
-                 int** part_ids_out, float** part_scores_out, cudaStream_t s);
+                 int64_t item_begin, int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
+                 int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, cudaStream_t s);
 
 static int mask_fields(const tgcn_graph* g, const int** rowptr, const int** col, int* row_begin, int* col_off) {
   if (g) {
@@ -420,9 +420,10 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
     float* part_scores;
     if (int rc = mask_fields(mask_graph, &mrowptr, &mcol, &mrow_begin, &mcol_off)) return rc;
     if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs,
-                              ldi, K, item_begin, item_end, k, d_workspace, workspace_bytes, &n_splits, &part_ids, &part_scores,
-                              (cudaStream_t)stream))
+                              ldi, K, item_begin, item_end, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes,
+                              &n_splits, &part_ids, &part_scores, (cudaStream_t)stream))
       return rc;
+    if (n_splits == 1) return 0;  // the kernel wrote (and completed) the final table itself
     return tgcn_topk_merge(mask_graph, n_rank, d_users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, stream);
   }
   EvalArgs a;

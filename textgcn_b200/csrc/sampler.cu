@@ -61,6 +61,31 @@ __global__ void __launch_bounds__(256) sample_bpr_kernel(const SampleArgs a) {
   }
 }
 
+// n2  Bernoulli(1 - p) edge keep-mask drawn on the device (replaces torch.rand(nnz) on the host + H2D, base_model.py:82):
+// one byte per nnz, 16 entries per thread from four 64-bit hashes, written as one 128-bit store.
+__global__ void __launch_bounds__(256) dropout_mask_kernel(long long n16, long long nnz, unsigned long long seed, uint32_t thresh,
+                                                           uint8_t* __restrict__ keep) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n16) return;
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const unsigned long long idx = (unsigned long long)t * 16 + q * 4 + b;
+      const uint32_t r = mix32(seed + idx * 0x9E3779B97F4A7C15ULL);
+      packed |= (r < thresh ? 1u : 0u) << (8 * b);
+    }
+    w[q] = packed;
+  }
+  if ((t + 1) * 16 <= nnz) {
+    *reinterpret_cast<uint4*>(keep + t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    for (long long i = t * 16; i < nnz; ++i) keep[i] = (uint8_t)((w[(i - t * 16) >> 2] >> (8 * ((i - t * 16) & 3))) & 0xff);
+  }
+}
+
 // a14  AdvSamplDataset.__getitem__ (advanced_sampling.py:21-22): n_cand DISTINCT uniform items per batch row.
 // Distinctness without a set: position q of row b maps through a keyed 4-round Feistel permutation of [0, 2^bits)
 // with cycle walking back into [0, n_items), i.e. the first n_cand entries of a random permutation of the items.
@@ -116,6 +141,18 @@ __global__ void __launch_bounds__(256) sample_positives_kernel(const int* __rest
 }  // namespace tgcn
 
 using namespace tgcn;
+
+extern "C" int tgcn_dropout_mask(int64_t nnz, float dropout, uint64_t seed, uint8_t* d_keep, tgcn_stream_t stream) {
+  TGCN_REQUIRE(nnz > 0 && d_keep != nullptr, "bad arguments");
+  TGCN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout=%f out of [0,1)", dropout);
+  TGCN_REQUIRE(((uintptr_t)d_keep & 15) == 0, "keep mask must be 16-byte aligned");
+  const double keep_p = 1.0 - (double)dropout;
+  const uint32_t thresh = keep_p >= 1.0 ? 0xffffffffu : (uint32_t)(keep_p * 4294967296.0);
+  const long long n16 = (nnz + 15) / 16;
+  dropout_mask_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n16, nnz, (unsigned long long)seed, thresh, d_keep);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int tgcn_sample_positives(const tgcn_graph_t* g, int64_t batch, int32_t n_pos, const int32_t* d_users, uint64_t seed,
                                      int64_t* d_out, tgcn_stream_t stream) {

@@ -152,8 +152,10 @@ class B200HotPath:
         if not self.training or self.dropout <= 0:
             return None
         nnz = self.graph.nnz
-        if self.dropout_rng == "device":
-            return torch.rand(nnz, device=self.graph.device) < (1 - self.dropout)
+        if self.dropout_rng == "device":  # one kernel, counter-based hash keyed by torch's seed and a per-model draw counter
+            n = self.__dict__["_b200_mask_draws"] = self.__dict__.get("_b200_mask_draws", 0) + 1
+            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + n * 0xD6E8FEB86659FD93) & (2 ** 64 - 1)
+            return ops.dropout_mask(nnz, float(self.dropout), seed, self.graph.device)
         return (torch.rand(nnz) < (1 - self.dropout)).to(self.graph.device)
 
     def _single(self) -> bool:

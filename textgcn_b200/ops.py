@@ -168,6 +168,15 @@ def layer_mean(addends: Sequence[torch.Tensor], out: torch.Tensor, divisor: Opti
     return out
 
 
+def dropout_mask(nnz: int, dropout: float, seed: int, device) -> torch.Tensor:
+    """Bernoulli(1 - dropout) keep mask over nnz entries, drawn by one kernel on the device (uint8, 1 = keep)."""
+    lib = _lib.load()
+    keep = torch.empty(nnz, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        check(lib.tgcn_dropout_mask(nnz, float(dropout), seed & (2 ** 64 - 1), _ptr(keep), _stream()))
+    return keep
+
+
 def _keep_u8(keep: torch.Tensor) -> torch.Tensor:
     if keep.dtype == torch.bool:
         keep = keep.view(torch.uint8)

@@ -4,6 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            # ours (N>1: launched by torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port), rank 0 only
 
+Why two workloads: BASELINE.json quotes the metric on configs[1] for one GPU (the tier's N = 1 rule) and asks for the
+1/2/4/8-GPU series on the 200M-edge graph (configs[4]).  The N = 1 line therefore reports c2 at the top level and ALSO
+carries `c5_single_gpu` (the base of the scaling series); every N > 1 line carries `n1_same_workload`, the same c5 workload
+timed on one GPU inside the same run, so scaling ratios are like-for-like.
+
 A "step" is one pass of the hot path over the whole graph: ``representation`` = L fused SpMM layers + layer mean.
 ``value`` = nnz(Â)·L / t with inputs resident in HBM; ``e2e`` = the same through the host-buffer C-ABI call
 (``tgcn_propagate_host``: H2D of E0, L layers, D2H of the result).  Workloads (``config.workload``):
@@ -44,6 +49,7 @@ def parse():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="N = 1: skip the extra 200M-edge (configs[4]) single-GPU leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the adv_sampling / LTR legs (BASELINE.json configs[2], [3])")
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--no-l2-hints", action="store_true", help="disable the L2 cache-policy hints of the SpMM (A/B comparison)")
@@ -178,6 +184,26 @@ def train_leg(w, graph, dev, flush, torch, batch=2048, steps=10, warmup=3):
     return {"ms_per_step": ms, "batch": batch, "dropout": params.dropout, "steps_per_s": 1e3 / ms,
             "includes": "device dropout draw, L-layer propagate, fused BPR(SELU)+L2 kernel, Horner backward (L transposed SpMM), "
                         "fused Adam over both tables"}
+
+
+def c5_single_gpu_leg(dev, flush, torch, topk, hbm_peak):
+    """The multi-GPU workload (configs[4]) on ONE GPU, so the N = 1 line also carries the base of the scaling series."""
+    from textgcn_b200 import ops
+    w = build_workload("c5", dev)
+    nu, ni, d, L, nnz = w["nu"], w["ni"], w["d"], w["L"], w["nnz"]
+    n = nu + ni
+    graph = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    t = timed_steps(lambda: ops.propagate_fwd(graph, w["uw"], w["iw"], L, out=out), 3, 1, flush, torch)
+    ms = sum(t) / len(t)
+    step_bytes = L * spmm_layer_bytes(nnz, n, d) + L * n * 4 * d
+    users = torch.arange(16384, dtype=torch.int32, device=dev)
+    te = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], topk, users=users), 2, 1, flush, torch)
+    ems = sum(te) / len(te)
+    ach = step_bytes / (ms * 1e-3) / 1e9
+    return {"workload": "c5", "n_users": nu, "n_items": ni, "nnz": nnz, "emb": d, "layers": L, "ms_per_step": ms,
+            "edges_per_s": nnz * L / (ms * 1e-3), "roofline_achieved_GBs": ach, "roofline_frac": ach / hbm_peak,
+            "eval_users_per_s": len(users) / (ems * 1e-3), "eval_tensor_flops_per_s": 3 * 2.0 * d * ni * len(users) / (ems * 1e-3)}
 
 
 def extras_leg(w, graph, dev, flush, torch, batch=2048):
@@ -594,6 +620,16 @@ def main():
             extra["n1_same_workload"] = {"error": str(exc)[:200]}
     if world > 1:
         dist.barrier()
+
+    if world == 1 and name == "c2" and not args.no_c5:
+        try:
+            del graph, out
+            for key in ("rowptr", "col", "val"):
+                w[key] = w[key].cpu()  # keep what the CPU baseline needs, free the device copies
+            torch.cuda.empty_cache()
+            extra["c5_single_gpu"] = c5_single_gpu_leg(dev, flush, torch, args.topk, hbm_peak)
+        except Exception as exc:
+            extra["c5_single_gpu"] = {"error": str(exc)[:300]}
 
     if rank == 0:
         per_rank_bytes = step_bytes / world

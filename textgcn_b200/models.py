@@ -97,11 +97,10 @@ class _FusedBprFn(torch.autograd.Function):
         g = ctx.graph
         grad_emb, grad_w0 = ctx.grad_emb, ctx.grad_w0
         ctx.grad_emb = ctx.grad_w0 = None
-        gb, gr = g_losses.tolist()  # the reference syncs every step anyway (isnan assert, base_model.py:123)
-        if gb != 1.0:
-            grad_emb.mul_(gb)
-        if gr != 1.0:
-            grad_w0.mul_(gr)
+        # scale by the upstream gradients ON THE DEVICE (0-dim operands, no host sync): two O(N·d) elementwise passes are
+        # far cheaper than draining the stream to read two floats
+        grad_emb.mul_(g_losses[0])
+        grad_w0.mul_(g_losses[1])
         ops.propagate_bwd(g, grad_emb, ctx.n_layers, ctx.single, ctx.keep, ctx.dropout, grad_in=grad_w0, accumulate=True)
         return (grad_w0[:g.n_users], grad_w0[g.n_users:]) + (None,) * 9
 
@@ -307,6 +306,7 @@ class BaseModel(B200HotPath, nn.Module):
         self.fused_adam = getattr(params, "fused_adam", False)
         self.dropout_rng = getattr(params, "dropout_rng", "host")
         self.eval_precision = getattr(params, "eval_precision", "auto")
+        self.nan_check = getattr(params, "nan_check", "step")
 
     def _copy_dataset_params(self, dataset):
         self.n_users = dataset.n_users
@@ -359,13 +359,18 @@ class BaseModel(B200HotPath, nn.Module):
             self.training = True
             self._loss_values = defaultdict(float)
             epoch_loss = 0
+            nan_seen = torch.zeros((), dtype=torch.bool, device=self.device)
             for data in batches:
                 self.optimizer.zero_grad()
                 batch_loss = self.get_loss(data)
-                assert not batch_loss.isnan(), f"loss is NA at epoch {epoch}"
+                if self.nan_check == "step":  # the reference's per-step device sync (base_model.py:123)
+                    assert not batch_loss.isnan(), f"loss is NA at epoch {epoch}"
+                else:                          # same check without draining the stream every step
+                    nan_seen |= batch_loss.detach().isnan()
                 epoch_loss += batch_loss.detach()
                 batch_loss.backward()
                 self.optimizer.step()
+            assert not bool(nan_seen), f"loss is NA at epoch {epoch}"
             if epoch % self.evaluate_every:
                 continue
             self.logger.info(f"Epoch {epoch}: {' '.join([f'{k} = {float(v):.4f}' for k, v in self._loss_values.items()])}")

@@ -587,3 +587,18 @@ def test_device_dropout_mask_statistics(ops):
             assert abs(agree - (p * p + (1 - p) ** 2)) < 5e-3              # independent draws
             lag = float((k1[1:] == k1[:-1]).float().mean())
             assert abs(lag - (p * p + (1 - p) ** 2)) < 5e-3                # no serial correlation
+
+
+@pytest.mark.parametrize("n_rank,n_items,d,k", [(200, 900, 64, 100), (150, 1200, 48, 20), (64, 3000, 160, 10)])
+def test_eval_auto_precision_falls_back_to_exact_kernel(ops, n_rank, n_items, d, k):
+    """k > 64, K not a multiple of 32 or K > 128 are outside the tensor-core kernel: "auto" must route to the exact
+    fp32 kernel (bit-exact on the dyadic fixture) and an explicit "3xtf32" request must fail loudly, not silently."""
+    from textgcn_b200 import TgcnError
+    rng = np.random.default_rng(k)
+    ue = (rng.integers(-32, 33, size=(n_rank, d)) / 16).astype(np.float32)
+    ie = (rng.integers(-8, 9, size=(n_items, d)) / 16).astype(np.float32)
+    ids, sc = ops.eval_topk(None, _cuda(ue), _cuda(ie), k)
+    o_ids, o_sc = O.canonical_topk(ue.astype(np.float64) @ ie.astype(np.float64).T, k)
+    assert np.array_equal(ids.cpu().numpy(), o_ids) and np.array_equal(sc.cpu().numpy(), o_sc.astype(np.float32))
+    with pytest.raises(TgcnError):
+        ops.eval_topk(None, _cuda(ue), _cuda(ie), k, precision="3xtf32")

@@ -84,7 +84,7 @@ __device__ __forceinline__ bool is_masked(const EvalArgs& a, int user, int item)
   return sorted_contains(a.mcol, __ldg(a.mrowptr + r), __ldg(a.mrowptr + r + 1), item + a.mcol_off);
 }
 
-__global__ void __launch_bounds__(kEvalThreads) eval_topk_simt_kernel(const EvalArgs a) {
+__global__ void __launch_bounds__(kEvalThreads, 1) eval_topk_simt_kernel(const EvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);             // [BK][BM+PAD]
   float* Bs = As + BK * (BM + PAD);                            // [BK][BN+PAD]

@@ -259,7 +259,12 @@ def extras_leg(w, graph, dev, flush, torch, batch=2048):
     t = timed_steps(lambda: ltr.predict_device(torch.arange(n_eval, dtype=torch.int32, device=dev)), 2, 1, flush, torch)
     ms = sum(t) / len(t)
     out["ltr_pop"] = {"users_per_s": n_eval / (ms * 1e-3), "ms": ms, "n_users_ranked": n_eval, "text_dim": D, "contraction_width": w["d"] + 2 * D,
-                      "includes": "propagate, ltr_pack_items/users, eval_topk_simt_kernel (K = d + 2D, fp32 FMA) with per-user/item bias, merge"}
+                      "tensor_flops_per_s": 3 * 2.0 * (w["d"] + 2 * D) * w["ni"] * n_eval / (ms * 1e-3),
+                      "includes": "propagate, ltr_pack_items/users, tf32_split_kernel x2, eval_topk_tc_kernel<128,20,2,stream> (3xTF32, user and "
+                                  "item K-chunks streamed together, bias terms folded into one extra K-chunk)"}
+    ltr.eval_precision = "fp32"
+    t = timed_steps(lambda: ltr.predict_device(torch.arange(n_eval, dtype=torch.int32, device=dev)), 2, 1, flush, torch)
+    out["ltr_pop"]["fp32_simt_users_per_s"] = n_eval / (sum(t) / len(t) * 1e-3)
     return out
 
 

@@ -133,8 +133,10 @@ int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch,
  * Items the user interacted with in `mask_graph` (user rows of Â = train_user_dict) are excluded;
  * when fewer than k unmasked items exist the list is completed with masked items, lowest id first,
  * score -inf.  Order is the canonical strict order (score desc, item id asc).
- * precision: 1 = exact fp32 FMA (SIMT kernel); 2 = 3xTF32 on the tcgen05 tensor cores (K % 32 == 0, K <= 128, no bias;
- * scores within ~1e-6 norm-wise of fp32, bit-exact for TF32-representable inputs); 0 = 3xTF32 when eligible, else fp32.
+ * precision: 1 = exact fp32 FMA (SIMT kernel); 2 = 3xTF32 on the tcgen05 tensor cores (k <= 64; K is zero-padded to whole
+ * 32-wide chunks, bias terms ride in one extra chunk; the user tile stays resident in shared memory for K <= 128 and is
+ * streamed with the item tile above that; scores within ~1e-6 norm-wise of fp32, bit-exact for TF32-representable
+ * inputs); 0 = 3xTF32 when eligible, else fp32.
  * Outputs (n_rank, k) int32 ids and fp32 scores.  k <= TGCN_MAX_TOPK. */
 int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
 int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users,

@@ -194,7 +194,27 @@ def test_topk_bit_exact_on_exact_arithmetic(ops, n_rank, n_items, d, k, precisio
     assert np.array_equal(m_ids.cpu().numpy(), o_ids) and np.array_equal(m_sc.cpu().numpy(), o_sc)
 
 
-@pytest.mark.parametrize("d,n_items,k", [(64, 9000, 20), (128, 3000, 40), (32, 1500, 20)])
+@pytest.mark.parametrize("n_rank,n_items,d,k", [(150, 1200, 48, 20), (64, 3000, 160, 10), (130, 700, 1600, 20), (40, 900, 260, 33)])
+def test_3xtf32_wide_and_ragged_contractions_with_bias(ops, n_rank, n_items, d, k):
+    """Zero-padded K (not a multiple of 32), the streamed-user-tile variant (K > 128, the LTR width 1600) and the bias
+    chunk: bit-exact on the dyadic fixture (bias values dyadic too), against both the oracle and the fp32 kernel."""
+    rng = np.random.default_rng(d)
+    ue = (rng.integers(-16, 17, size=(n_rank, d)) / 16).astype(np.float32)
+    ie = (rng.integers(-8, 9, size=(n_items, d)) / 16).astype(np.float32)
+    ub = (rng.integers(-64, 65, size=n_rank) / 8).astype(np.float32)
+    ib = (rng.integers(-64, 65, size=n_items) / 8).astype(np.float32)
+    ref = ue.astype(np.float64) @ ie.astype(np.float64).T
+    for bias in (False, True):
+        full = ref + (ub[:, None].astype(np.float64) + ib[None, :] if bias else 0.0)
+        o_ids, o_sc = O.canonical_topk(full, k)
+        kw = dict(user_bias=_cuda(ub), item_bias=_cuda(ib)) if bias else {}
+        for precision in ("3xtf32", "fp32"):
+            ids, sc = ops.eval_topk(None, _cuda(ue), _cuda(ie), k, precision=precision, **kw)
+            assert np.array_equal(ids.cpu().numpy(), o_ids), (bias, precision)
+            assert np.array_equal(sc.cpu().numpy(), o_sc.astype(np.float32)), (bias, precision)
+
+
+@pytest.mark.parametrize("d,n_items,k", [(64, 9000, 20), (128, 3000, 40), (32, 1500, 20), (1600, 2500, 20)])
 def test_3xtf32_scores_within_stated_tolerance(ops, d, n_items, k):
     """The tensor-core path (3xTF32) against fp64: |Δscore| <= 1e-5·‖u‖‖i‖, ids tie-aware."""
     gen = torch.Generator().manual_seed(d)
@@ -589,10 +609,10 @@ def test_device_dropout_mask_statistics(ops):
             assert abs(lag - (p * p + (1 - p) ** 2)) < 5e-3                # no serial correlation
 
 
-@pytest.mark.parametrize("n_rank,n_items,d,k", [(200, 900, 64, 100), (150, 1200, 48, 20), (64, 3000, 160, 10)])
+@pytest.mark.parametrize("n_rank,n_items,d,k", [(200, 900, 64, 100), (150, 1200, 48, 65)])
 def test_eval_auto_precision_falls_back_to_exact_kernel(ops, n_rank, n_items, d, k):
-    """k > 64, K not a multiple of 32 or K > 128 are outside the tensor-core kernel: "auto" must route to the exact
-    fp32 kernel (bit-exact on the dyadic fixture) and an explicit "3xtf32" request must fail loudly, not silently."""
+    """k > 64 is outside the tensor-core kernel (register-resident lists): "auto" must route to the exact fp32 kernel
+    (bit-exact on the dyadic fixture) and an explicit "3xtf32" request must fail loudly, not silently."""
     from textgcn_b200 import TgcnError
     rng = np.random.default_rng(k)
     ue = (rng.integers(-32, 33, size=(n_rank, d)) / 16).astype(np.float32)

@@ -148,15 +148,18 @@ __device__ __forceinline__ void reg_list_insert(float (&ls)[KL], int (&li)[KL], 
 // BN = item rows per tile, KL = list capacity (>= k), EW = epilogue warps per TMEM lane quarter.  With EW = 2 the two
 // warps of a quarter read the same 32 lanes but own 16 user rows each, which halves the chain of (warp-serialised)
 // list updates — the epilogue's critical path, since hits are rare but divergent.
-template <int BN, int KL, int EW>
+// STREAM = false: the user tile [hi | lo] stays resident in shared memory for the whole sweep (K <= 128).
+// STREAM = true : wide contractions (the LTR score, K = d + 2D + bias chunk): user and item K-chunks travel together
+//                 through the ring, one stage = {U_hi, U_lo, I_hi, I_lo} of one 32-wide K-chunk (12 MMAs per stage).
+template <int BN, int KL, int EW, bool STREAM>
 __global__ void __launch_bounds__(128 + 128 * EW, 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int KC = a.K / TC_CHUNK;
-  const int n_a = 2 * KC;
-  constexpr int B_STAGE_BYTES = BN * 128;
+  const int n_a = STREAM ? 0 : 2 * KC;  // resident user chunks
+  constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BN * 128 : BN * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
   float* stage_v = reinterpret_cast<float*>(gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES);  // [128][36]
@@ -202,10 +205,28 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer: resident user tile, then the item chunks of every tile ----
-      mbar_expect_tx(bar_a_full, n_a * TC_A_CHUNK_BYTES);
-      for (int c = 0; c < n_a; ++c) tma_load_2d(sA + c * TC_A_CHUNK_BYTES, &map_u, bar_a_full, c * TC_CHUNK, m0);
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (STREAM) {
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+          const int row0 = tile * BN;
+          for (int kc = 0; kc < KC; ++kc) {
+            const uint32_t st = sB + stage * B_STAGE_BYTES, full = bar_b_full + 8 * stage;
+            mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full, B_STAGE_BYTES);
+            tma_load_2d(st, &map_u, full, kc * TC_CHUNK, m0);
+            tma_load_2d(st + TC_A_CHUNK_BYTES, &map_u, full, a.K + kc * TC_CHUNK, m0);
+            tma_load_2d(st + 2 * TC_A_CHUNK_BYTES, &map_i, full, kc * TC_CHUNK, row0);
+            tma_load_2d(st + 2 * TC_A_CHUNK_BYTES + BN * 128, &map_i, full, a.K + kc * TC_CHUNK, row0);
+            if (++stage == a.n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      } else {
+      mbar_expect_tx(bar_a_full, n_a * TC_A_CHUNK_BYTES);
+      for (int c = 0; c < n_a; ++c) tma_load_2d(sA + c * TC_A_CHUNK_BYTES, &map_u, bar_a_full, c * TC_CHUNK, m0);
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int row0 = tile * BN;
         for (int c = 0; c < n_a; ++c) {  // order: hi_0, lo_0, hi_1, lo_1, ...
@@ -219,13 +240,16 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           }
         }
       }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- MMA issuer: D[128 x BN] (+)= A[128 x 8] · B[BN x 8]ᵀ, kind::tf32, fp32 accumulate in TMEM ----
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      mbar_wait(bar_a_full, 0);
-      tc_fence_after();
+      if constexpr (!STREAM) {
+        mbar_wait(bar_a_full, 0);
+        tc_fence_after();
+      }
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -233,6 +257,28 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         uint32_t accumulate = 0;
+        if constexpr (STREAM) {
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar_b_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t st = sB + stage * B_STAGE_BYTES;
+            const uint32_t a_hi = st, a_lo = st + TC_A_CHUNK_BYTES, b_hi = st + 2 * TC_A_CHUNK_BYTES, b_lo = b_hi + BN * 128;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_hi + kk * 32), idesc, accumulate);
+              accumulate = 1;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(b_hi + kk * 32), idesc, 1);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_lo + kk * 32), idesc, 1);
+            umma_commit(bar_b_empty + 8 * stage);
+            if (++stage == a.n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
         for (int c = 0; c < n_a; ++c) {
           mbar_wait(bar_b_full + 8 * stage, phase);
           tc_fence_after();
@@ -391,17 +437,32 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   }
 }
 
-// out row r = [hi(x) | lo(x)] of source row (rows ? rows[r] : row_begin + r); K floats each half.
+// out row r = [hi(x), hi(bias chunk) | lo(x), lo(bias chunk)] of source row (rows ? rows[r] : row_begin + r); each half is
+// Kp = K (+ 32 when bias terms exist) floats.  The optional bias chunk folds `score += user_bias[u] + item_bias[i]` into
+// the contraction: the user side carries [ub, 1, 0, ...] and the item side [1, ib, 0, ...], so no epilogue work is needed.
 __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict__ src, int64_t ld, const int* __restrict__ rows,
-                                                         int64_t row_begin, int64_t n_rows, int K, float* __restrict__ out) {
-  const int k4 = K >> 2;
+                                                         int64_t row_begin, int64_t n_rows, int K, int Kp,
+                                                         const float* __restrict__ bias, const int* __restrict__ bias_rows,
+                                                         int64_t bias_begin, int item_side, int bias_chunk, float* __restrict__ out) {
+  const int k4 = Kp >> 2;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_rows * k4) return;
   const int64_t r = t / k4;
   const int c = (int)(t % k4) * 4;
-  const int64_t sr = rows ? (int64_t)__ldg(rows + r) : row_begin + r;
-  const float4 x = ldg4(src + sr * ld + c);
-  float xs[4] = {x.x, x.y, x.z, x.w}, hi[4], lo[4];
+  float xs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < K) {
+    const int64_t sr = rows ? (int64_t)__ldg(rows + r) : row_begin + r;
+    const float4 x = ldg4(src + sr * ld + c);
+    xs[0] = x.x;
+    xs[1] = x.y;
+    xs[2] = x.z;
+    xs[3] = x.w;
+  } else if (c == Kp - TC_CHUNK && bias_chunk) {
+    const float b = bias ? __ldg(bias + (bias_rows ? (int64_t)__ldg(bias_rows + r) : bias_begin + r)) : 0.f;
+    xs[0] = item_side ? 1.f : b;
+    xs[1] = item_side ? b : 1.f;
+  }
+  float hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint32_t h, l;
@@ -411,8 +472,8 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
     lo[i] = __uint_as_float(l);
   }
-  *reinterpret_cast<float4*>(out + r * 2 * K + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<float4*>(out + r * 2 * K + K + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<float4*>(out + r * 2 * Kp + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(out + r * 2 * Kp + Kp + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -445,62 +506,83 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t co
 
 static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 
-// Shared-memory plan for the tensor-core kernel; returns 0 stages when it does not fit (caller falls back).
-static void tc_plan(int K, int k, int* bn, int* n_stages, size_t* smem) {
-  *bn = K <= 64 ? 256 : 128;
-  const size_t a_bytes = (size_t)(2 * (K / TC_CHUNK)) * TC_A_CHUNK_BYTES;
+// Shared-memory plan for the tensor-core kernel (Kp = contraction width incl. the bias chunk); 0 stages = does not fit.
+static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream) {
+  *stream = Kp > 128;
+  *bn = (*stream || Kp > 64) ? 128 : 256;
+  const size_t a_bytes = *stream ? 0 : (size_t)(2 * (Kp / TC_CHUNK)) * TC_A_CHUNK_BYTES;
   const size_t fixed = 1024 /*align slack*/ + a_bytes + (size_t)TC_BM * TC_VSTRIDE * 4 + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
   const size_t budget = 227 * 1024;
-  const size_t stage = (size_t)*bn * 128;
+  const size_t stage = *stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)*bn * 128 : (size_t)*bn * 128;
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
   *n_stages = s;
   *smem = fixed + (size_t)s * stage;
 }
 
-bool eval_tc_eligible(int64_t K, int32_t k) {
-  if (K % TC_CHUNK != 0 || K > 128 || K <= 0 || k > 64) return false;  // register-resident lists: k <= 64
+// contraction width as the kernel sees it: K rounded up to whole 32-wide chunks (zero padded) + one chunk for the bias terms
+static inline int tc_padded_k(int64_t K, bool has_bias) { return (int)((K + TC_CHUNK - 1) / TC_CHUNK) * TC_CHUNK + (has_bias ? TC_CHUNK : 0); }
+
+bool eval_tc_eligible(int64_t K, int32_t k, bool has_bias) {
+  if (K % 4 != 0 || K <= 0 || K > 8192 || k > 64) return false;  // register-resident lists: k <= 64
   int bn, st;
   size_t sm;
-  tc_plan((int)K, k, &bn, &st, &sm);
+  bool stream;
+  tc_plan(tc_padded_k(K, has_bias), &bn, &st, &sm, &stream);
   return st >= 2;
 }
 
-int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, int n_splits) {
-  return al256(n_rank * 2 * K * 4) + al256(n_range * 2 * K * 4) + al256((int64_t)n_splits * n_rank * k * 4) * 2 + 256;
+int eval_tc_tile_n(int64_t K, bool has_bias) {
+  int bn, st;
+  size_t sm;
+  bool stream;
+  tc_plan(tc_padded_k(K, has_bias), &bn, &st, &sm, &stream);
+  return bn;
+}
+
+int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, bool has_bias, int n_splits) {
+  const int64_t Kp = tc_padded_k(K, has_bias);
+  return al256(n_rank * 2 * Kp * 4) + al256(n_range * 2 * Kp * 4) + al256((int64_t)n_splits * n_rank * k * 4) * 2 + 256;
 }
 
 void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_splits, int* tiles_per_split);
 
 int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
                  int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
-                 int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
-                 int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, cudaStream_t s) {
+                 int64_t item_end, const float* d_user_bias, const float* d_item_bias, int32_t k, int finalize, int* d_out_ids,
+                 float* d_out_scores, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
+                 float** part_scores_out, cudaStream_t s) {
+  const bool has_bias = d_user_bias != nullptr || d_item_bias != nullptr;
+  const int Kp = tc_padded_k(K, has_bias);
   int bn, n_stages;
   size_t smem;
-  tc_plan((int)K, k, &bn, &n_stages, &smem);
-  TGCN_REQUIRE(n_stages >= 2, "3xTF32 path does not fit in shared memory for K=%lld k=%d", (long long)K, k);
+  bool stream;
+  tc_plan(Kp, &bn, &n_stages, &smem, &stream);
+  TGCN_REQUIRE(n_stages >= 2, "3xTF32 path does not fit in shared memory for K=%lld", (long long)K);
   const int64_t n_range = item_end - item_begin;
   int n_splits, tps;
   eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
-  const int64_t need = eval_tc_workspace_bytes(n_rank, n_range, K, k, n_splits);
+  const int64_t need = eval_tc_workspace_bytes(n_rank, n_range, K, k, has_bias, n_splits);
   TGCN_REQUIRE(d_workspace && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
   char* ws = (char*)d_workspace;
   float* u2 = (float*)ws;
-  float* i2 = (float*)(ws + al256(n_rank * 2 * K * 4));
-  int* part_ids = (int*)((char*)i2 + al256(n_range * 2 * K * 4));
+  float* i2 = (float*)(ws + al256(n_rank * 2 * (int64_t)Kp * 4));
+  int* part_ids = (int*)((char*)i2 + al256(n_range * 2 * (int64_t)Kp * 4));
   float* part_scores = (float*)((char*)part_ids + al256((int64_t)n_splits * n_rank * k * 4));
-  const int k4 = (int)K / 4;
-  tf32_split_kernel<<<(unsigned)((n_rank * k4 + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, by_pos ? nullptr : d_users, 0, n_rank, (int)K, u2);
+  const int k4 = Kp / 4;
+  // user operand: rows gathered by user id unless already packed in list order; user bias follows the same indexing
+  tf32_split_kernel<<<(unsigned)((n_rank * k4 + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, by_pos ? nullptr : d_users, 0, n_rank, (int)K, Kp,
+                                                                         d_user_bias, by_pos ? nullptr : d_users, 0, 0, has_bias ? 1 : 0, u2);
   TGCN_CHECK_LAUNCH();
-  tf32_split_kernel<<<(unsigned)((n_range * k4 + 255) / 256), 256, 0, s>>>(d_item_vecs, ldi, nullptr, item_begin, n_range, (int)K, i2);
+  tf32_split_kernel<<<(unsigned)((n_range * k4 + 255) / 256), 256, 0, s>>>(d_item_vecs, ldi, nullptr, item_begin, n_range, (int)K, Kp, d_item_bias,
+                                                                          nullptr, item_begin, 1, has_bias ? 1 : 0, i2);
   TGCN_CHECK_LAUNCH();
   CUtensorMap map_u, map_i;
-  if (int rc = make_map(&map_u, u2, n_rank, 2 * K, TC_BM)) return rc;
-  if (int rc = make_map(&map_i, i2, n_range, 2 * K, bn)) return rc;
+  if (int rc = make_map(&map_u, u2, n_rank, 2 * (int64_t)Kp, TC_BM)) return rc;
+  if (int rc = make_map(&map_i, i2, n_range, 2 * (int64_t)Kp, bn)) return rc;
   TcArgs a;
   a.n_rank = (int)n_rank;
-  a.K = (int)K;
+  a.K = Kp;
   a.n_range = (int)n_range;
   a.item_begin = (int)item_begin;
   a.k = k;
@@ -518,21 +600,23 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   a.out_ids = d_out_ids;
   a.out_scores = d_out_scores;
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
-#define TGCN_TC_LAUNCH(BN_, KL_, EW_)                                                                                        \
+#define TGCN_TC_LAUNCH(BN_, KL_, EW_, ST_)                                                                                   \
   do {                                                                                                                       \
-    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    eval_topk_tc_kernel<BN_, KL_, EW_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                               \
+    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    eval_topk_tc_kernel<BN_, KL_, EW_, ST_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                          \
   } while (0)
-  static const int ew20 = getenv("TGCN_TC_EW") ? atoi(getenv("TGCN_TC_EW")) : 2;  // tuning knob (2 or 4 warps per lane quarter)
-  if (bn == 256) {
-    if (k <= 20 && ew20 == 4) TGCN_TC_LAUNCH(256, 20, 4);
-    else if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2);
-    else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2);
-    else TGCN_TC_LAUNCH(256, 64, 1);
+  if (stream) {
+    if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2, true);
+    else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2, true);
+    else TGCN_TC_LAUNCH(128, 64, 1, true);
+  } else if (bn == 256) {
+    if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2, false);
+    else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2, false);
+    else TGCN_TC_LAUNCH(256, 64, 1, false);
   } else {
-    if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2);
-    else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2);
-    else TGCN_TC_LAUNCH(128, 64, 1);
+    if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2, false);
+    else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2, false);
+    else TGCN_TC_LAUNCH(128, 64, 1, false);
   }
 #undef TGCN_TC_LAUNCH
   TGCN_CHECK_LAUNCH();

@@ -332,12 +332,14 @@ void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_split
 }
 
 // tensor-core path (eval_tc.cu)
-bool eval_tc_eligible(int64_t K, int32_t k);
-int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, int n_splits);
+bool eval_tc_eligible(int64_t K, int32_t k, bool has_bias);
+int eval_tc_tile_n(int64_t K, bool has_bias);
+int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, bool has_bias, int n_splits);
 int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
-                 int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K,
-                 int64_t item_begin, int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
-                 int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, cudaStream_t s);
+                 int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
+                 int64_t item_end, const float* d_user_bias, const float* d_item_bias, int32_t k, int finalize, int* d_out_ids,
+                 float* d_out_scores, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
+                 float** part_scores_out, cudaStream_t s);
 
 static int mask_fields(const tgcn_graph* g, const int** rowptr, const int** col, int* row_begin, int* col_off) {
   if (g) {
@@ -366,9 +368,12 @@ int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t
   int ns, tps;
   eval_split_plan(n_rank, n_items_range, BN, &ns, &tps);
   int64_t need = (int64_t)ns * n_rank * k * 8 + 512;
-  if (eval_tc_eligible(K, k)) {
-    eval_split_plan(n_rank, n_items_range, K <= 64 ? 256 : 128, &ns, &tps);
-    const int64_t tc = eval_tc_workspace_bytes(n_rank, n_items_range, K, k, ns);
+  if (eval_tc_eligible(K, k, true)) {  // sized for the widest variant (with the bias chunk)
+    eval_split_plan(n_rank, n_items_range, eval_tc_tile_n(K, true), &ns, &tps);
+    int64_t tc = eval_tc_workspace_bytes(n_rank, n_items_range, K, k, true, ns);
+    eval_split_plan(n_rank, n_items_range, eval_tc_tile_n(K, false), &ns, &tps);
+    const int64_t tc2 = eval_tc_workspace_bytes(n_rank, n_items_range, K, k, true, ns);
+    if (tc2 > tc) tc = tc2;
     if (tc > need) need = tc;
   }
   return need;
@@ -410,8 +415,8 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
   TGCN_REQUIRE(precision >= 0 && precision <= 2, "precision must be 0 (auto), 1 (fp32) or 2 (3xTF32)");
   const int64_t need = tgcn_eval_workspace_bytes(n_rank, item_end - item_begin, K, k);
   TGCN_REQUIRE(d_workspace && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
-  const bool tc_ok = eval_tc_eligible(K, k) && !d_user_bias && !d_item_bias && ldu % 4 == 0 && ldi % 4 == 0;
-  TGCN_REQUIRE(precision != 2 || tc_ok, "3xTF32 path needs K %% 32 == 0, K <= 128, no bias terms and a k that fits shared memory");
+  const bool tc_ok = eval_tc_eligible(K, k, d_user_bias || d_item_bias) && ldu % 4 == 0 && ldi % 4 == 0;
+  TGCN_REQUIRE(precision != 2 || tc_ok, "3xTF32 path needs k <= 64 (and K <= 8192)");
   if (tc_ok && precision != 1) {
     const int* mrowptr;
     const int* mcol;
@@ -420,8 +425,8 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
     float* part_scores;
     if (int rc = mask_fields(mask_graph, &mrowptr, &mcol, &mrow_begin, &mcol_off)) return rc;
     if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs,
-                              ldi, K, item_begin, item_end, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes,
-                              &n_splits, &part_ids, &part_scores, (cudaStream_t)stream))
+                              ldi, K, item_begin, item_end, d_user_bias, d_item_bias, k, finalize, d_out_ids, d_out_scores, d_workspace,
+                              workspace_bytes, &n_splits, &part_ids, &part_scores, (cudaStream_t)stream))
       return rc;
     if (n_splits == 1) return 0;  // the kernel wrote (and completed) the final table itself
     return tgcn_topk_merge(mask_graph, n_rank, d_users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, stream);

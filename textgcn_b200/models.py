@@ -558,7 +558,7 @@ class B200LTR:
             user_bias = (user_bias.double() + w[5] * pop[0][users.long(), 0].double()).float().contiguous()
             item_bias = (w[6] * pop[1][:, 0].double()).float().contiguous()
         return ops.eval_topk(self.graph, users_p, items_p, k, users=users, user_bias=user_bias, item_bias=item_bias,
-                             by_position=True)
+                             by_position=True, precision=self.eval_precision)
 
 
 class LTRLinear(B200LTR, BaseModel):

@@ -54,8 +54,14 @@ def parse():
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--no-l2-hints", action="store_true", help="disable the L2 cache-policy hints of the SpMM (A/B comparison)")
     ap.add_argument("--ar-chunks", type=int, default=1, help="bipartite scheme: split the item-table all-reduce into this many chunks")
-    ap.add_argument("--mg-scheme", default="bipartite", choices=["bipartite", "rowblock"],
-                    help="multi-GPU propagation: users partitioned + item-table all-reduce, or row blocks + all-gather")
+    ap.add_argument("--mg-scheme", default="grid", choices=["grid", "bipartite", "rowblock"],
+                    help="multi-GPU propagation: G feature slices x R user partitions with a peer-memory result exchange (grid), "
+                         "users partitioned + item-table all-reduce (bipartite = grid 1xN without the final exchange), or row "
+                         "blocks + all-gather of layer embeddings (rowblock)")
+    ap.add_argument("--grid", default="auto", help="grid scheme shape GxR (G·R = N); auto = 2x1, 2x2, 4x2 for N = 2, 4, 8")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "collective"], help="grid scheme: result exchange through peer "
+                    "memory (fused into the last passes) or NCCL all-to-all / all-gather")
+    ap.add_argument("--nccl-high-priority", action="store_true", help="run the row-group all-reduce on a high-priority stream")
     return ap.parse_args()
 
 
@@ -403,6 +409,46 @@ def main():
         launches_per_step = L
         parallelism = "single GPU"
         scaling = "weak"
+    elif args.mg_scheme == "grid":
+        if args.grid == "auto":
+            G, R = {2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
+        else:
+            G, R = (int(x) for x in args.grid.lower().split("x"))
+        assert G * R == world, f"--grid {G}x{R} does not match {world} ranks"
+        gpart = tdist.GridPartition(w["rowptr"], nu, ni, d, G, R)
+        gg, rr = gpart.coords(rank)
+        row_group = None
+        for g_id in range(G):  # every rank creates every row group, in the same order
+            opts = None
+            if args.nccl_high_priority:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            grp = dist.new_group(gpart.row_group_ranks(g_id), pg_options=opts) if R > 1 else None
+            if g_id == gg:
+                row_group = grp
+        u0, u1 = gpart.rows.users(rr)
+        ugraph = ops.Graph(nu, ni, *gpart.rows.user_block(rr, w["rowptr"], w["col"], w["val"]), row_begin=u0, block=True)
+        igraph = ops.Graph(nu, ni, *gpart.rows.item_block(rr, w["rowptr"], w["col"], w["val"]), row_begin=nu, block=True)
+        prop = tdist.GridPropagator(gpart, rank, ugraph, igraph, L, dev, row_group=row_group, exchange=args.exchange)
+        c0, c1 = gpart.cols(gg)
+        e0_u = w["uw"][u0:u1, c0:c1].contiguous()
+        e0_i = w["iw"][:, c0:c1].contiguous()
+
+        def step():
+            prop.propagate(e0_u, e0_i)
+
+        dist.barrier()
+        sampler.start()
+        times = timed_steps(step, args.steps, args.warmup, flush, torch)
+        dist.barrier()
+        launches_per_step = 2 * L + 1
+        parallelism = (f"grid {G}x{R}: {G} feature slices of {gpart.ds} columns x {R} user partitions by nnz; per hop one NCCL "
+                       f"all-reduce of the (I, {gpart.ds}) item slice inside each row group of {R}; result exchange "
+                       f"{'fused into the last passes as peer-memory stores (CUDA IPC, NVLink)' if args.exchange == 'p2p' else 'by NCCL all-to-all + all-gather'}")
+        scaling = "strong"
+        extra["comm_bytes_per_hop_per_rank"] = prop.comm_bytes_per_hop
+        f0, f1 = gpart.final_users(rank)
+        rows_local = (f1 - f0) + ni
+        out_u, out_i = prop.out_u, prop.out_i
     elif args.mg_scheme == "rowblock":
         part = tdist.RowPartition(w["rowptr"], world)
         rp, col, val = part.local_block(rank, w["rowptr"], w["col"], w["val"])
@@ -476,6 +522,19 @@ def main():
 
             def e2e_step():
                 ops.propagate_host(graph, h_u, h_i, h_o, L, stage)
+        elif args.mg_scheme == "grid":
+            h_u = torch.empty_like(e0_u, device="cpu").pin_memory().copy_(e0_u.cpu())
+            h_i = torch.empty_like(e0_i, device="cpu").pin_memory().copy_(e0_i.cpu())
+            h_ou = torch.empty((f1 - f0, d), dtype=torch.float32).pin_memory()
+            h_oi = torch.empty((ni, d), dtype=torch.float32).pin_memory()
+            d_u, d_i = torch.empty_like(e0_u), torch.empty_like(e0_i)
+
+            def e2e_step():
+                d_u.copy_(h_u, non_blocking=True)
+                d_i.copy_(h_i, non_blocking=True)
+                ou, oi = prop.propagate(d_u, d_i)
+                h_ou.copy_(ou, non_blocking=True)
+                h_oi.copy_(oi, non_blocking=True)
         elif args.mg_scheme == "rowblock":
             h_e0 = torch.empty_like(e0, device="cpu").pin_memory().copy_(e0.cpu())
             h_o = torch.empty_like(out_local, device="cpu").pin_memory()
@@ -507,7 +566,8 @@ def main():
         if world == 1:
             rows_local = n
         e2e = {"value": nnz * L / (float(e_ms) * 1e-3), "unit": "edges/s", "ms_per_step": float(e_ms),
-               "h2d_bytes_per_step": rows_local * d * 4, "d2h_bytes_per_step": rows_local * d * 4,
+               "h2d_bytes_per_step": (e0_u.numel() + e0_i.numel()) * 4 if (world > 1 and args.mg_scheme == "grid") else rows_local * d * 4,
+               "d2h_bytes_per_step": rows_local * d * 4,
                "api": "tgcn_propagate_host (pinned host E0 -> device, L layers, result -> pinned host)" if world == 1
                else "host-pinned E0 shard -> device, L hops with the collective, result shard -> pinned host"}
 
@@ -546,6 +606,34 @@ def main():
 
                 def eval_step():
                     return ops.eval_topk(mgraph, u_tab, i_tab, k, users=sample)
+            elif args.mg_scheme == "grid":
+                per = min(per, gpart.final_users(world - 1)[1] - gpart.final_users(world - 1)[0])
+                n_eval = per * world
+                sample = torch.arange(f0, f0 + per, dtype=torch.int32, device=dev)  # global ids of this rank's first users
+                mrows = int(w["rowptr"][nu])
+                mgraph = ops.Graph(nu, ni, w["rowptr"][:nu + 1].contiguous(), w["col"][:mrows].contiguous(),
+                                   w["val"][:mrows].contiguous(), row_begin=0, block=True)
+                out_u_eval = out_u[:per]
+
+                def eval_step():
+                    return ops.eval_topk(mgraph, out_u_eval, out_i, k, users=sample, by_position=True)
+
+                all_users = torch.empty(n_eval, dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(all_users, sample)
+                all_vecs = torch.empty((n_eval, d), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(all_vecs, out_u_eval.contiguous())
+
+                def eval_item_sharded():
+                    return tdist.sharded_eval_topk(mgraph, all_vecs, out_i, all_users, k, rank, world, by_position=True)
+
+                a_ids, a_sc = eval_step()
+                b_ids, b_sc = eval_item_sharded()
+                extra["item_sharded_matches_user_sharded"] = bool(torch.equal(a_ids, b_ids) and torch.equal(a_sc, b_sc))
+                t_is = timed_steps(eval_item_sharded, args.eval_steps, 1, flush, torch)
+                is_ms = torch.tensor([sum(t_is) / len(t_is)], dtype=torch.float64, device=dev)
+                dist.all_reduce(is_ms, op=dist.ReduceOp.MAX)
+                extra["eval_item_sharded"] = {"users_per_s": n_eval / (float(is_ms) * 1e-3), "ms": float(is_ms),
+                                              "sharding": f"item range x{world}, all-to-all of partial top-k + merge"}
             else:
                 per = min(per, u1 - u0)
                 n_eval = per * world

@@ -29,6 +29,7 @@ extern "C" {
 
 #define TGCN_ABI_VERSION 1
 #define TGCN_MAX_LAYERS 15
+#define TGCN_MAX_PEERS 8
 #define TGCN_MAX_TOPK 128
 #define TGCN_ADV_MAX_CANDIDATES 2048
 
@@ -95,6 +96,44 @@ int tgcn_layer_mean(int64_t n, int32_t n_add, const float* const* h_add, float d
 int tgcn_propagate_fwd(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single,
                        const float* d_user_w, const float* d_item_w, const uint8_t* d_keep, float dropout,
                        float* d_out, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* e (multi-GPU)  representation with the FEATURE dimension sliced across GPUs.  E' = Â·E acts on every column
+ * independently, so GPU p can run all L hops on columns [col_off, col_off + d_slice) of the d_full-wide tables with no
+ * exchange between hops: d_user_slice (n_users, d_slice) and d_item_slice (n_items, d_slice) are its contiguous column
+ * slices of the layer-0 tables, the graph handle is the whole Â (replicated).  The exchange is fused into the LAST pass:
+ * its epilogue stores the layer mean (or the last layer if single) directly into the row-sharded full-width result
+ * tables of the peers through peer-mapped pointers (tgcn_peer_open): user row r goes to
+ * h_peer_user_out[r / users_per_rank] at local row r % users_per_rank, item rows go to every h_peer_item_out[q]
+ * (n_items, d_full), both at column col_off.  After a barrier every GPU holds users_emb for its user range and the whole
+ * items_emb, as base_model.py:106 returns them.  n_peers = 1 with local pointers assembles slices on one GPU. */
+int tgcn_propagate_sliced(const tgcn_graph_t* g, int64_t d_slice, int32_t n_layers, int32_t single,
+                          const float* d_user_slice, const float* d_item_slice, const uint8_t* d_keep, float dropout,
+                          int64_t d_full, int64_t col_off, int32_t n_peers, int64_t users_per_rank,
+                          float* const* h_peer_user_out, float* const* h_peer_item_out, void* d_workspace,
+                          int64_t workspace_bytes, tgcn_stream_t stream);
+
+/* The two building blocks of the GRID scheme (feature slices x user partitions; textgcn_b200.dist.GridPropagator), where
+ * the hops run through tgcn_spmm_ex on row-block handles and only the last pass changes layout:
+ * spmm_scatter: one pass  (add_0 + ... + Â_block·X) / divisor  whose rows go to the peers' full-width tables exactly as in
+ *   tgcn_propagate_sliced (global row id = the block's row_begin + local row);
+ * layer_mean_scatter: (add_0 + ... + add_{n_add-1}) / divisor over (n_rows, d_slice) tables, stored at column col_off of
+ *   rows [row0, row0 + n_rows) of every h_dst[q] (d_full-wide) — the item table's layer mean and its all-gather in one. */
+int tgcn_spmm_scatter(const tgcn_graph_t* g, int64_t d_slice, const float* d_x_user, const float* d_x_item, int32_t n_add,
+                      const float* const* h_add_user, const float* const* h_add_item, float divisor, int64_t d_full,
+                      int64_t col_off, int32_t n_peers, int64_t users_per_rank, float* const* h_peer_user_out,
+                      float* const* h_peer_item_out, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+int tgcn_layer_mean_scatter(int64_t n_rows, int64_t d_slice, int32_t n_add, const float* const* h_add, float divisor,
+                            int64_t d_full, int64_t col_off, int64_t row0, int32_t n_dst, float* const* h_dst,
+                            tgcn_stream_t stream);
+
+/* Peer memory for the call above (one process per GPU): tgcn_peer_alloc cudaMalloc's `bytes` on the current device and
+ * fills a 64-byte CUDA IPC handle the caller ships to the other ranks (any transport; torch.distributed here);
+ * tgcn_peer_open maps a peer's handle into this process (peer access enabled lazily); close / free undo them. */
+#define TGCN_PEER_HANDLE_BYTES 64
+int tgcn_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* h_handle);
+int tgcn_peer_open(const uint8_t* h_handle, void** d_ptr);
+int tgcn_peer_close(void* d_ptr);
+int tgcn_peer_free(void* d_ptr);
 
 /* Backward of the above (what autograd does at base_model.py:125 through :148/:157): given
  * d_grad_out = dL/d(out) (N, d) computes dL/dE0 into d_grad_in (N, d) with L transposed SpMMs in

@@ -119,6 +119,48 @@ def _worker(rank, world, port, case, ret):
         out_u2, out_i2 = torch.empty_like(out_u), torch.empty_like(out_i)
         cprop.propagate(e0[u0:u1].contiguous(), e0[nu:].contiguous(), out_u2, out_i2, single=bool(g["single"]))
         assert torch.equal(out_u2, out_u) and torch.equal(out_i2, out_i)
+        # feature-sliced scheme: all hops local on d/P columns, one exchange at the end (collective form under gloo)
+        if d % (4 * world) == 0:
+            fp = tdist.FeatureSlicePartition(nu, ni, d, world)
+            assert fp.users(0)[0] == 0 and fp.users(world - 1)[1] == nu and fp.cols(world - 1)[1] == d
+
+            def _cpu_local(graph, us, its, n_layers, single, out):
+                rp_, col_, val_ = graph
+                x = torch.cat([us, its])
+                layers = [x]
+                for _ in range(n_layers):
+                    layers.append(_cpu_spmm((rp_, col_, val_), layers[-1], torch.empty_like(x), [], 1.0))
+                out.copy_(layers[-1] if single else torch.mean(torch.stack(layers), dim=0))
+                return out
+
+            sp = tdist.SlicedPropagator(fp, rank, (rowptr, col, val), L, "cpu", exchange="collective", local_fn=_cpu_local)
+            us, its = fp.slice_tables(rank, e0[:nu], e0[nu:])
+            s_u, s_i = sp.propagate(us, its, single=bool(g["single"]))
+            f0, f1 = fp.users(rank)
+            assert s_u.shape == (f1 - f0, d) and s_i.shape == (ni, d)
+            assert np.abs(s_u.numpy() - g["rep_user"][f0:f1]).max() / np.abs(g["rep_user"]).max() < 1e-6
+            assert np.abs(s_i.numpy() - g["rep_item"]).max() / np.abs(g["rep_item"]).max() < 1e-6
+            # grid scheme on 2 ranks, both degenerate shapes: 2 slices x 1 row part, 1 slice x 2 row parts
+            mean_cpu = lambda adds, out, div: out.copy_(sum(adds[1:], adds[0]) / div)  # noqa: E731
+            for G_, R_ in ((2, 1), (1, 2)):
+                gp = tdist.GridPartition(rowptr, nu, ni, d, G_, R_)
+                gg, rr = gp.coords(rank)
+                row_group = None
+                for g_id in range(G_):  # every rank creates every group, in the same order
+                    grp = dist.new_group(gp.row_group_ranks(g_id))
+                    if g_id == gg:
+                        row_group = grp
+                ugb = gp.rows.user_block(rr, rowptr, col, val)
+                igb = gp.rows.item_block(rr, rowptr, col, val)
+                gprop = tdist.GridPropagator(gp, rank, ugb, igb, L, "cpu", row_group=row_group, exchange="collective",
+                                             spmm_fn=_cpu_spmm, mean_fn=mean_cpu)
+                c0, c1 = gp.cols(gg)
+                gu0, gu1 = gp.rows.users(rr)
+                g_u, g_i = gprop.propagate(e0[gu0:gu1, c0:c1].contiguous(), e0[nu:, c0:c1].contiguous(), single=bool(g["single"]))
+                h0, h1 = gp.final_users(rank)
+                assert g_u.shape == (h1 - h0, d) and g_i.shape == (ni, d)
+                assert np.abs(g_u.numpy() - g["rep_user"][h0:h1]).max() / np.abs(g["rep_user"]).max() < 1e-6, (G_, R_)
+                assert np.abs(g_i.numpy() - g["rep_item"]).max() / np.abs(g["rep_item"]).max() < 1e-6, (G_, R_)
         # item-sharded eval with cross-rank merge
         k = int(max(g["ks"]))
         tl = golden_lists(g)

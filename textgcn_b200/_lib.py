@@ -34,6 +34,16 @@ SIGNATURES = {
                                c_float, c_int32, _P, _P, c_int64, _P]),
     "tgcn_layer_mean": (c_int32, [c_int64, c_int32, POINTER(c_void_p), c_float, _P, _P]),
     "tgcn_propagate_fwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_float, _P, _P, c_int64, _P]),
+    "tgcn_propagate_sliced": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_float, c_int64, c_int64, c_int32, c_int64,
+                                        POINTER(c_void_p), POINTER(c_void_p), _P, c_int64, _P]),
+    "tgcn_spmm_scatter": (c_int32, [_P, c_int64, _P, _P, c_int32, POINTER(c_void_p), POINTER(c_void_p), c_float, c_int64, c_int64,
+                                    c_int32, c_int64, POINTER(c_void_p), POINTER(c_void_p), _P, c_int64, _P]),
+    "tgcn_layer_mean_scatter": (c_int32, [c_int64, c_int64, c_int32, POINTER(c_void_p), c_float, c_int64, c_int64, c_int64, c_int32,
+                                          POINTER(c_void_p), _P]),
+    "tgcn_peer_alloc": (c_int32, [c_int64, POINTER(c_void_p), _P]),
+    "tgcn_peer_open": (c_int32, [_P, POINTER(c_void_p)]),
+    "tgcn_peer_close": (c_int32, [_P]),
+    "tgcn_peer_free": (c_int32, [_P]),
     "tgcn_propagate_bwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, c_float, c_int32, _P, _P, c_int64, _P]),
     "tgcn_propagate_host": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, c_int64, _P]),
     "tgcn_bpr_workspace_bytes": (c_int64, [c_int64]),

@@ -68,6 +68,8 @@ struct tgcn_graph {
   int mask_col_off;  // eval masks: entry value = mask_col_off + item id (n_users unless overridden)
   int l2_hints;   // allow L2 cache-policy hints on large tables
   int hot_rows;   // rows [0, hot_rows) gather from the small, skewed table (item table): keep those lines in L2
+  int* order;      // owned: rows with <= kSplitThreshold non-zeros, user rows then item rows, each by decreasing
+  int n_ordered;   //        number of kUnroll-wide steps (stable), so the lane groups sharing a warp finish together
   int bipartite;  // verified at creation: user rows reference only item columns and vice versa
 };
 

@@ -102,6 +102,30 @@ static int build_segments(tgcn_graph* g, cudaStream_t stream) {
       splits.push_back(sr);
     }
   }
+  // processing order of the short rows: stable counting sort by (user/item phase, steps descending)
+  {
+    constexpr int kStep = 4;  // kUnroll of the SpMM kernels
+    const int n_keys = kSplitThreshold / kStep + 1;
+    const int64_t phase_split = g->is_block ? g->n_rows : g->n_users;
+    std::vector<int> count(2 * n_keys + 1, 0);
+    auto key_of = [&](int64_t r, int deg) { return (r < phase_split ? 0 : n_keys) + (n_keys - 1 - (deg + kStep - 1) / kStep); };
+    for (int64_t r = 0; r < g->n_rows; ++r) {
+      const int deg = rowptr[r + 1] - rowptr[r];
+      if (deg <= kSplitThreshold) count[key_of(r, deg) + 1]++;
+    }
+    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+    std::vector<int> order(count.back());
+    for (int64_t r = 0; r < g->n_rows; ++r) {
+      const int deg = rowptr[r + 1] - rowptr[r];
+      if (deg <= kSplitThreshold) order[count[key_of(r, deg)]++] = (int)r;
+    }
+    g->n_ordered = (int)order.size();
+    if (!order.empty()) {
+      TGCN_CHECK_CUDA(cudaMalloc(&g->order, sizeof(int) * order.size()));
+      TGCN_CHECK_CUDA(cudaMemcpyAsync(g->order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, stream));
+      TGCN_CHECK_CUDA(cudaStreamSynchronize(stream));
+    }
+  }
   g->max_degree = max_deg;
   g->n_segments = (int)segs.size();
   g->n_split_rows = (int)splits.size();
@@ -149,6 +173,8 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->col = d_col;
   g->val = d_val;
   g->tperm = nullptr;
+  g->order = nullptr;
+  g->n_ordered = 0;
   g->segments = nullptr;
   g->split_rows = nullptr;
   g->split_counters = nullptr;
@@ -210,6 +236,7 @@ int tgcn_graph_build_transpose_perm(tgcn_graph_t* g, tgcn_stream_t stream) {
 void tgcn_graph_destroy(tgcn_graph_t* g) {
   if (!g) return;
   if (g->tperm) cudaFree(g->tperm);
+  if (g->order) cudaFree(g->order);
   if (g->segments) cudaFree(g->segments);
   if (g->split_rows) cudaFree(g->split_rows);
   if (g->split_counters) cudaFree(g->split_counters);

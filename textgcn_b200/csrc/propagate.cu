@@ -24,6 +24,17 @@ struct Epilogue {
   int add_split;
   float divisor;
   int accumulate;
+  // Feature-sliced multi-GPU mode (tgcn_propagate_sliced): this launch computes columns [col_off, col_off + d) of
+  // d_full-wide rows and stores them straight into the row-sharded, full-width result tables of the peer GPUs
+  // (peer memory over NVLink): user row r goes to its owner r / users_per_rank, item rows go to every peer.
+  int n_peers;  // 0 = plain store into y
+  int row_base;
+  int users_per_rank;
+  int n_users;
+  int d_full;
+  int col_off;
+  float* peer_user[TGCN_MAX_PEERS];
+  float* peer_item[TGCN_MAX_PEERS];
 };
 
 struct SpmmArgs {
@@ -40,6 +51,8 @@ struct SpmmArgs {
   int hot_rows;  // rows [0, hot_rows) gather from a table worth keeping in L2 (evict_last); -1 = no cache hints
   int hint_mode;  // bit 0: evict_last on hot gathers, bit 1: evict_first on cold gathers, bit 2: evict_first on col/val
   int n_rows;
+  int n_units;       // row units of the group / slice kernels: n_rows, or the number of short rows when `order` is set
+  const int* order;  // short rows (<= kSplitThreshold non-zeros) by decreasing step count, or NULL
   int d;
   const Segment* segments;
   int n_segments;
@@ -66,6 +79,18 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int row, int c
     s.y /= ep.divisor;
     s.z /= ep.divisor;
     s.w /= ep.divisor;
+  }
+  if (ep.n_peers > 0) {
+    const size_t coff = (size_t)ep.col_off + off;
+    const int grow = row + ep.row_base;  // global row id (row blocks start at row_base)
+    if (grow < ep.n_users) {
+      const int q = grow / ep.users_per_rank;
+      *reinterpret_cast<float4*>(ep.peer_user[q] + (size_t)(grow - q * ep.users_per_rank) * ep.d_full + coff) = s;
+    } else {
+      const size_t o = (size_t)(grow - ep.n_users) * ep.d_full + coff;
+      for (int q = 0; q < ep.n_peers; ++q) *reinterpret_cast<float4*>(ep.peer_item[q] + o) = s;
+    }
+    return;
   }
   float4* out = reinterpret_cast<float4*>(a.y + (size_t)row * a.d + off);
   if (ep.accumulate) add4(s, *out);
@@ -263,7 +288,10 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     split = s.split;
   } else {
     row = unit - a.n_segments;
-    if (row >= a.n_rows) return;
+    if (row >= (LPN < 32 ? a.n_units : a.n_rows)) return;
+    // several rows share a warp when LPN < 32: `order` lists the short rows by decreasing step count so that
+    // the lane groups of a warp finish together (ncu: 16 of 32 lanes active on the 16-wide slice without it)
+    if (LPN < 32 && a.order) row = __ldg(a.order + row);
     begin = __ldg(a.rowptr + row);
     end = __ldg(a.rowptr + row + 1);
     slot = -1;
@@ -283,9 +311,8 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     pol_x = row < a.hot_rows ? ((a.hint_mode & 1) ? l2_policy_evict_last() : normal)
                              : ((a.hint_mode & 2) ? l2_policy_evict_first() : normal);
   }
-  for (int p = begin; p < end; p += kUnroll) {
-    int c[kUnroll];
-    float v[kUnroll];
+  // col/val of step p (c < 0: no gather — past the row end or a dropped edge)
+  auto load_cv = [&](int p, int (&c)[kUnroll], float (&v)[kUnroll]) {
 #pragma unroll
     for (int i = 0; i < kUnroll; ++i) {
       const bool ok = p + i < end;
@@ -307,6 +334,13 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
         }
       }
     }
+  };
+  // (Prefetching step p + 1's col/val ahead of step p's gathers was measured slower everywhere: 48 registers instead
+  // of 40 cost more occupancy than the shorter dependent chain returned — c5 120.2 -> 124.5 ms, c2 0.371 -> 0.392 ms.)
+  for (int p = begin; p < end; p += kUnroll) {
+    int c[kUnroll];
+    float v[kUnroll];
+    load_cv(p, c, v);
     float4 x[kUnroll][VPL];
 #pragma unroll
     for (int i = 0; i < kUnroll; ++i)
@@ -362,9 +396,38 @@ __global__ void __launch_bounds__(256) layer_mean_kernel(const MeanArgs m, int64
   *reinterpret_cast<float4*>(out + i * 4) = s;
 }
 
+struct MeanScatterArgs {
+  MeanArgs m;
+  int ds4;       // float4 per source row
+  int d_full;    // destination row stride (floats)
+  int col_off;   // destination column (floats)
+  int64_t row0;  // destination row of source row 0
+  int n_dst;
+  float* dst[TGCN_MAX_PEERS];
+};
+
+// Same mean over (rows, ds) tables, stored at column col_off of the d_full-wide rows [row0, row0 + rows) of n_dst
+// destination tables (the peers' replicated items_emb): the all-gather of the feature-sliced scheme as plain stores.
+__global__ void __launch_bounds__(256) layer_mean_scatter_kernel(const MeanScatterArgs a, int64_t n4) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = ldg4(a.m.add[0] + i * 4);
+  for (int t = 1; t < a.m.n_add; ++t) add4(s, ldg4(a.m.add[t] + i * 4));
+  if (a.m.divisor != 1.0f) {
+    s.x /= a.m.divisor;
+    s.y /= a.m.divisor;
+    s.z /= a.m.divisor;
+    s.w /= a.m.divisor;
+  }
+  const int64_t r = i / a.ds4;
+  const int c4 = (int)(i - r * a.ds4);
+  const size_t o = (size_t)(a.row0 + r) * a.d_full + a.col_off + c4 * 4;
+  for (int q = 0; q < a.n_dst; ++q) *reinterpret_cast<float4*>(a.dst[q] + o) = s;
+}
+
 template <int LPN, int VPL>
 static void launch_group(const SpmmArgs& a, cudaStream_t s) {
-  const int64_t units = (int64_t)a.n_segments + a.n_rows;
+  const int64_t units = (int64_t)a.n_segments + (LPN < 32 ? a.n_units : a.n_rows);
   const int64_t blocks = (units * LPN + kGroupThreads - 1) / kGroupThreads;
   if (a.hot_rows >= 0) spmm_group_kernel<LPN, VPL, true><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
   else spmm_group_kernel<LPN, VPL, false><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
@@ -412,6 +475,12 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.keep_div = 1.f;
   a.keep_scale = 1.f;
   a.n_rows = (int)g->n_rows;
+  {
+    const char* m = getenv("TGCN_ROW_ORDER");  // A/B switch: 0 = rows in natural order
+    const bool use = g->order != nullptr && !(m && atoi(m) == 0);
+    a.order = use ? g->order : nullptr;
+    a.n_units = use ? g->n_ordered : (int)g->n_rows;
+  }
   a.d = (int)d;
   a.segments = g->segments;
   a.n_segments = g->n_segments;
@@ -421,6 +490,7 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.ep.add_split = g->is_block ? 0x7fffffff : (int)g->n_users;
   a.ep.divisor = 1.f;
   a.ep.accumulate = 0;
+  a.ep.n_peers = 0;
   a.x_split = g->is_block ? 0x7fffffff : (int)g->n_users;
   // cache hints only pay when the gathered tables exceed L2 (~126 MB); hot_rows < 0 disables them
   {
@@ -430,9 +500,21 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.hot_rows = (g->l2_hints && a.hint_mode != 0 && (int64_t)(g->n_users + g->n_items) * d * 4 > (96ll << 20)) ? g->hot_rows : -1;
 }
 
+struct ScatterSpec {  // destination of the last pass in feature-sliced mode (see Epilogue)
+  int n_peers, users_per_rank, d_full, col_off;
+  float* const* peer_user;
+  float* const* peer_item;
+};
+
 }  // namespace tgcn
 
 using namespace tgcn;
+
+static int spmm_ex_impl(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const float* d_x_item,
+                        const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
+                        const float* const* h_add_user, const float* const* h_add_item, float divisor,
+                        int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream,
+                        const ScatterSpec* sc);
 
 extern "C" {
 
@@ -449,8 +531,19 @@ int tgcn_spmm_ex(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const 
                  const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
                  const float* const* h_add_user, const float* const* h_add_item, float divisor,
                  int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream) {
+  return spmm_ex_impl(g, d, d_x_user, d_x_item, d_keep, dropout, transposed, n_add, h_add_user, h_add_item, divisor,
+                      accumulate, d_y, d_workspace, workspace_bytes, stream, nullptr);
+}
+
+}  // extern "C"
+
+static int spmm_ex_impl(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const float* d_x_item,
+                        const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
+                        const float* const* h_add_user, const float* const* h_add_item, float divisor,
+                        int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream,
+                        const ScatterSpec* sc) {
   if (int rc = check_common(g, d, 1)) return rc;
-  TGCN_REQUIRE(d_x_user && d_y, "NULL x or y");
+  TGCN_REQUIRE(d_x_user && (d_y || sc), "NULL x or y");
   TGCN_REQUIRE(n_add >= 0 && n_add <= kMaxAddends, "n_add=%d out of range", n_add);
   const int64_t need = align_up((int64_t)g->n_segments * d * sizeof(float), 256);
   TGCN_REQUIRE(g->n_segments == 0 || (d_workspace && workspace_bytes >= need), "workspace too small: need %lld bytes", (long long)need);
@@ -477,8 +570,27 @@ int tgcn_spmm_ex(const tgcn_graph_t* g, int64_t d, const float* d_x_user, const 
   a.ep.accumulate = accumulate;
   a.partial = (float*)d_workspace;
   a.y = d_y;
+  if (sc) {
+    TGCN_REQUIRE(!accumulate, "feature-sliced scatter cannot accumulate");
+    TGCN_REQUIRE(sc->n_peers >= 1 && sc->n_peers <= TGCN_MAX_PEERS, "n_peers=%d out of range [1, %d]", sc->n_peers, TGCN_MAX_PEERS);
+    TGCN_REQUIRE(sc->users_per_rank > 0 && (int64_t)sc->users_per_rank * sc->n_peers >= g->n_users, "users_per_rank does not cover the users");
+    TGCN_REQUIRE(sc->d_full % 4 == 0 && sc->col_off % 4 == 0 && sc->col_off + d <= sc->d_full, "bad column slice");
+    a.ep.n_peers = sc->n_peers;
+    a.ep.row_base = (int)g->row_begin;
+    a.ep.users_per_rank = sc->users_per_rank;
+    a.ep.n_users = (int)g->n_users;
+    a.ep.d_full = sc->d_full;
+    a.ep.col_off = sc->col_off;
+    for (int q = 0; q < sc->n_peers; ++q) {
+      TGCN_REQUIRE(sc->peer_user[q] && sc->peer_item[q], "NULL peer table %d", q);
+      a.ep.peer_user[q] = sc->peer_user[q];
+      a.ep.peer_item[q] = sc->peer_item[q];
+    }
+  }
   return launch_spmm(g, a, (cudaStream_t)stream);
 }
+
+extern "C" {
 
 int tgcn_layer_mean(int64_t n, int32_t n_add, const float* const* h_add, float divisor, float* d_out, tgcn_stream_t stream) {
   TGCN_REQUIRE(n > 0 && n % 4 == 0, "n=%lld must be a positive multiple of 4", (long long)n);
@@ -496,17 +608,60 @@ int tgcn_layer_mean(int64_t n, int32_t n_add, const float* const* h_add, float d
   return 0;
 }
 
+int tgcn_layer_mean_scatter(int64_t n_rows, int64_t d_slice, int32_t n_add, const float* const* h_add, float divisor,
+                            int64_t d_full, int64_t col_off, int64_t row0, int32_t n_dst, float* const* h_dst,
+                            tgcn_stream_t stream) {
+  TGCN_REQUIRE(n_rows > 0 && d_slice > 0 && d_slice % 4 == 0, "bad source shape");
+  TGCN_REQUIRE(n_add >= 1 && n_add <= kMaxAddends && h_add, "bad addends");
+  TGCN_REQUIRE(d_full % 4 == 0 && col_off % 4 == 0 && col_off >= 0 && col_off + d_slice <= d_full && row0 >= 0, "bad destination geometry");
+  TGCN_REQUIRE(n_dst >= 1 && n_dst <= TGCN_MAX_PEERS && h_dst, "n_dst=%d out of range [1, %d]", n_dst, TGCN_MAX_PEERS);
+  MeanScatterArgs a;
+  a.m.n_add = n_add;
+  for (int t = 0; t < n_add; ++t) {
+    TGCN_REQUIRE(h_add[t] != nullptr, "NULL addend %d", t);
+    a.m.add[t] = h_add[t];
+  }
+  a.m.divisor = divisor;
+  a.ds4 = (int)(d_slice / 4);
+  a.d_full = (int)d_full;
+  a.col_off = (int)col_off;
+  a.row0 = row0;
+  a.n_dst = n_dst;
+  for (int q = 0; q < n_dst; ++q) {
+    TGCN_REQUIRE(h_dst[q] != nullptr, "NULL destination %d", q);
+    a.dst[q] = h_dst[q];
+  }
+  const int64_t n4 = n_rows * (d_slice / 4);
+  layer_mean_scatter_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, n4);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
+
+int tgcn_spmm_scatter(const tgcn_graph_t* g, int64_t d_slice, const float* d_x_user, const float* d_x_item, int32_t n_add,
+                      const float* const* h_add_user, const float* const* h_add_item, float divisor, int64_t d_full,
+                      int64_t col_off, int32_t n_peers, int64_t users_per_rank, float* const* h_peer_user_out,
+                      float* const* h_peer_item_out, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream) {
+  TGCN_REQUIRE(h_peer_user_out && h_peer_item_out, "NULL peer table list");
+  TGCN_REQUIRE(users_per_rank > 0 && users_per_rank < (1ll << 31) && d_full > 0 && d_full <= 4096, "bad slice geometry");
+  ScatterSpec sc{n_peers, (int)users_per_rank, (int)d_full, (int)col_off, h_peer_user_out, h_peer_item_out};
+  return spmm_ex_impl(g, d_slice, d_x_user, d_x_item, nullptr, 0.f, 0, n_add, h_add_user, h_add_item, divisor, 0, nullptr,
+                      d_workspace, workspace_bytes, stream, &sc);
+}
+
 int tgcn_spmm_fwd(const tgcn_graph_t* g, int64_t d, const float* d_x, float* d_y, void* d_workspace,
                   int64_t workspace_bytes, tgcn_stream_t stream) {
   return tgcn_spmm_ex(g, d, d_x, nullptr, nullptr, 0.f, 0, 0, nullptr, nullptr, 1.f, 0, d_y, d_workspace, workspace_bytes, stream);
 }
 
-int tgcn_propagate_fwd(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* d_user_w,
-                       const float* d_item_w, const uint8_t* d_keep, float dropout, float* d_out, void* d_workspace,
-                       int64_t workspace_bytes, tgcn_stream_t stream) {
+}  // extern "C"
+
+static int propagate_fwd_impl(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* d_user_w,
+                              const float* d_item_w, const uint8_t* d_keep, float dropout, float* d_out, void* d_workspace,
+                              int64_t workspace_bytes, tgcn_stream_t stream, const ScatterSpec* sc) {
   if (int rc = check_common(g, d, n_layers)) return rc;
   TGCN_REQUIRE(!g->is_block, "propagate_fwd needs a whole-graph handle; drive row blocks with tgcn_spmm_ex");
-  TGCN_REQUIRE(d_user_w && d_item_w && d_out, "NULL table pointer");
+  TGCN_REQUIRE(d_user_w && d_item_w && (d_out || sc), "NULL table pointer");
+  TGCN_REQUIRE(!sc || n_layers >= 1, "feature-sliced propagation needs n_layers >= 1");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t N = g->n_rows;
   if (n_layers == 0) {
@@ -540,11 +695,32 @@ int tgcn_propagate_fwd(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32
       divisor = (float)(n_layers + 1);
     }
     float* y = last ? d_out : buf(l - 1);
-    if (int rc = tgcn_spmm_ex(g, d, xu, xi, d_keep, dropout, 0, n_add, add_u, add_i, divisor, 0, y, partial,
-                              workspace_bytes - ((char*)partial - ws), stream))
+    if (int rc = spmm_ex_impl(g, d, xu, xi, d_keep, dropout, 0, n_add, add_u, add_i, divisor, 0, y, partial,
+                              workspace_bytes - ((char*)partial - ws), stream, last ? sc : nullptr))
       return rc;
   }
   return 0;
+}
+
+extern "C" {
+
+int tgcn_propagate_fwd(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* d_user_w,
+                       const float* d_item_w, const uint8_t* d_keep, float dropout, float* d_out, void* d_workspace,
+                       int64_t workspace_bytes, tgcn_stream_t stream) {
+  return propagate_fwd_impl(g, d, n_layers, single, d_user_w, d_item_w, d_keep, dropout, d_out, d_workspace, workspace_bytes,
+                            stream, nullptr);
+}
+
+int tgcn_propagate_sliced(const tgcn_graph_t* g, int64_t d_slice, int32_t n_layers, int32_t single,
+                          const float* d_user_slice, const float* d_item_slice, const uint8_t* d_keep, float dropout,
+                          int64_t d_full, int64_t col_off, int32_t n_peers, int64_t users_per_rank,
+                          float* const* h_peer_user_out, float* const* h_peer_item_out, void* d_workspace,
+                          int64_t workspace_bytes, tgcn_stream_t stream) {
+  TGCN_REQUIRE(h_peer_user_out && h_peer_item_out, "NULL peer table list");
+  TGCN_REQUIRE(users_per_rank > 0 && users_per_rank < (1ll << 31) && d_full > 0 && d_full <= 4096, "bad slice geometry");
+  ScatterSpec sc{n_peers, (int)users_per_rank, (int)d_full, (int)col_off, h_peer_user_out, h_peer_item_out};
+  return propagate_fwd_impl(g, d_slice, n_layers, single, d_user_slice, d_item_slice, d_keep, dropout, nullptr, d_workspace,
+                            workspace_bytes, stream, &sc);
 }
 
 int tgcn_propagate_bwd(tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* d_grad_out,

@@ -228,6 +228,265 @@ class BipartitePropagator:
         return out_user_local, out_item
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Feature-sliced scheme: every GPU runs all L hops on d/P columns of the tables; ONE exchange, fused into the last pass
+# ---------------------------------------------------------------------------------------------------------
+class FeatureSlicePartition:
+    """E' = Â·E acts on each embedding column independently, so the hops need no exchange at all when the FEATURE
+    dimension is what is split: rank p owns columns [p·d/P, (p+1)·d/P) of both tables for every layer and a replica
+    of the CSR of Â (3.2 GB at the 200M-edge config; the tables, which dominate memory, shrink by P).  Only the
+    RESULT has to change layout — users_emb row-sharded by user range, items_emb replicated, both full width, which is
+    what eval sharding consumes — and that single exchange rides in the last SpMM's epilogue as peer-memory stores."""
+
+    def __init__(self, n_users: int, n_items: int, d: int, world_size: int):
+        if d % (4 * world_size) != 0:
+            raise ValueError(f"embedding width {d} must be a multiple of 4·world_size = {4 * world_size}")
+        self.n_users, self.n_items, self.d, self.world_size = n_users, n_items, d, world_size
+        self.ds = d // world_size
+        self.per = -(-n_users // world_size)  # users per rank (the last range may be short)
+
+    def cols(self, rank: int) -> Tuple[int, int]:
+        return rank * self.ds, (rank + 1) * self.ds
+
+    def users(self, rank: int) -> Tuple[int, int]:
+        return min(rank * self.per, self.n_users), min((rank + 1) * self.per, self.n_users)
+
+    def slice_tables(self, rank: int, user_w: torch.Tensor, item_w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        c0, c1 = self.cols(rank)
+        return user_w[:, c0:c1].contiguous(), item_w[:, c0:c1].contiguous()
+
+
+def _default_local_propagate(graph, user_slice, item_slice, n_layers, single, out):
+    from . import ops
+    return ops.propagate_fwd(graph, user_slice, item_slice, n_layers, single=single, out=out)
+
+
+class SlicedPropagator:
+    """K-layer propagation with the feature dimension sliced across ranks.
+
+    ``exchange="p2p"`` (default, CUDA only): the last pass stores the layer mean directly into the peers' result
+    tables (CUDA IPC peer memory, NVLink), bracketed by two stream-ordered barriers.  ``exchange="collective"``: the
+    unfused comparison — local (N, d/P) result, then all-to-all (user rows) + all-gather (item rows) + an interleave
+    copy; this is also the path the world_size-2 gloo test drives on CPU with the kernel stubbed."""
+
+    def __init__(self, part: FeatureSlicePartition, rank: int, graph, n_layers: int, device, group=None,
+                 exchange: str = "p2p", local_fn: Callable = _default_local_propagate):
+        self.part, self.rank, self.graph, self.n_layers, self.group = part, rank, graph, n_layers, group
+        self.exchange, self.local_fn = exchange, local_fn
+        P, d, ds = part.world_size, part.d, part.ds
+        u0, u1 = part.users(rank)
+        self.n_local = u1 - u0
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        if exchange == "p2p":
+            from . import ops
+            self._ops = ops
+            self.buf_u = ops.PeerBuffer(max(part.per, 1) * d * 4, device)
+            self.buf_i = ops.PeerBuffer(part.n_items * d * 4, device)
+            handles = [None] * P
+            if P > 1:
+                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle), group=group)
+            self.peer_u = [self.buf_u.ptr if q == rank else self.buf_u.open_peer(handles[q][0]) for q in range(P)]
+            self.peer_i = [self.buf_i.ptr if q == rank else self.buf_i.open_peer(handles[q][1]) for q in range(P)]
+            self.out_u = self.buf_u.tensor((max(part.per, 1), d))
+            self.out_i = self.buf_i.tensor((part.n_items, d))
+        elif exchange == "collective":
+            self.out_u = torch.empty((max(part.per, 1), d), dtype=torch.float32, device=device)
+            self.out_i = torch.empty((part.n_items, d), dtype=torch.float32, device=device)
+            self.local = torch.empty((part.n_users + part.n_items, ds), dtype=torch.float32, device=device)
+        else:
+            raise ValueError(f"unknown exchange {exchange!r}")
+        # sent per rank: its column slice of every user row to the owner and of every item row to all peers
+        self.comm_bytes_per_step = (part.n_users - self.n_local) * ds * 4 + (P - 1) * part.n_items * ds * 4
+
+    def _barrier(self) -> None:
+        """Stream-ordered barrier: returns (on the stream) once every rank's earlier work on its stream is complete."""
+        if self.part.world_size > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def propagate(self, user_slice: torch.Tensor, item_slice: torch.Tensor, single: bool = False):
+        """user_slice (n_users, d/P), item_slice (n_items, d/P): this rank's columns of E0.  Returns (users_emb rows of
+        this rank's user range (n_local, d), items_emb (n_items, d)); the tensors are reused by the next call."""
+        part, P = self.part, self.part.world_size
+        nu, ni, ds = part.n_users, part.n_items, part.ds
+        if self.exchange == "p2p":
+            self._barrier()  # every rank is done reading the previous result tables
+            self._ops.propagate_sliced(self.graph, user_slice, item_slice, self.n_layers, part.d, part.cols(self.rank)[0],
+                                       part.per, self.peer_u, self.peer_i, single=single)
+            self._barrier()  # every rank's stores have landed
+        else:
+            loc = self.local_fn(self.graph, user_slice, item_slice, self.n_layers, single, self.local)
+            n_my = self.n_local
+            if P > 1:
+                sizes_in = [part.users(q)[1] - part.users(q)[0] for q in range(P)]
+                recv = torch.empty((P * n_my, ds), dtype=loc.dtype, device=loc.device)
+                dist.all_to_all_single(recv, loc[:nu], output_split_sizes=[n_my] * P, input_split_sizes=sizes_in, group=self.group)
+                gath = torch.empty((P * ni, ds), dtype=loc.dtype, device=loc.device)
+                dist.all_gather_into_tensor(gath, loc[nu:].contiguous(), group=self.group)
+            else:
+                recv, gath = loc[:nu], loc[nu:]
+            self.out_u[:n_my].view(n_my, P, ds).copy_(recv.view(P, n_my, ds).transpose(0, 1))
+            self.out_i.view(ni, P, ds).copy_(gath.view(P, ni, ds).transpose(0, 1))
+        return self.out_u[:self.n_local], self.out_i
+
+    def close(self) -> None:
+        if self.exchange == "p2p":
+            self.buf_u.close()
+            self.buf_i.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Grid scheme: G feature slices x R user partitions (P = G·R); all-reduce only inside a row group of R ranks
+# ---------------------------------------------------------------------------------------------------------
+class GridPartition:
+    """rank = g·R + r.  Feature slice g owns columns [g·d/G, (g+1)·d/G) of every table; inside a slice the R ranks of a
+    ROW GROUP split the users by nnz (BipartitePartition) and all-reduce the slice of the item table once per hop —
+    (I, d/G) floats among R ranks instead of (I, d) among P.  G = P is the pure feature-sliced scheme (no exchange per
+    hop, but d/P-wide rows: 64-byte gathers run HBM at ~60 % of its streaming rate), G = 1 the bipartite scheme (full
+    rows, the largest all-reduce); in between both costs shrink.  The RESULT layout is the same for every G x R:
+    users_emb rows [rank·per, (rank+1)·per) full width on each rank, items_emb replicated."""
+
+    def __init__(self, rowptr: torch.Tensor, n_users: int, n_items: int, d: int, n_slices: int, n_row_parts: int):
+        if d % (4 * n_slices) != 0:
+            raise ValueError(f"embedding width {d} must be a multiple of 4·G = {4 * n_slices}")
+        self.G, self.R = n_slices, n_row_parts
+        self.world_size = n_slices * n_row_parts
+        self.n_users, self.n_items, self.d, self.ds = n_users, n_items, d, d // n_slices
+        self.rows = BipartitePartition(rowptr, n_users, n_items, n_row_parts)
+        self.per = -(-n_users // self.world_size)
+
+    def coords(self, rank: int) -> Tuple[int, int]:
+        return rank // self.R, rank % self.R
+
+    def cols(self, g: int) -> Tuple[int, int]:
+        return g * self.ds, (g + 1) * self.ds
+
+    def final_users(self, rank: int) -> Tuple[int, int]:
+        return min(rank * self.per, self.n_users), min((rank + 1) * self.per, self.n_users)
+
+    def row_group_ranks(self, g: int) -> List[int]:
+        return [g * self.R + r for r in range(self.R)]
+
+
+class GridPropagator:
+    """K-layer propagation on a G x R grid.  The hops are BipartitePropagator's (on d/G-wide tables, all-reduce in
+    ``row_group``); the change of layout rides in the last passes: ``exchange="p2p"`` — the last user-row SpMM stores
+    each row into its final owner's table and the item table's layer mean is stored into every rank's replica (peer
+    memory, NVLink), each row-group member broadcasting 1/R of the rows; ``exchange="collective"`` — the same through
+    all-to-all / all-gather on ``group`` (the comparison arm, and what the gloo test drives on CPU)."""
+
+    def __init__(self, part: GridPartition, rank: int, user_graph, item_graph, n_layers: int, device, row_group=None,
+                 group=None, exchange: str = "p2p", spmm_fn: Callable = _default_spmm, mean_fn: Callable = _default_mean):
+        self.part, self.rank, self.group, self.exchange = part, rank, group, exchange
+        self.g, self.r = part.coords(rank)
+        self._spmm_fn, self._mean_fn = spmm_fn, mean_fn
+        self.inner = BipartitePropagator(part.rows, self.r, user_graph, item_graph, part.ds, n_layers, device, group=row_group,
+                                         spmm_fn=self._spmm, mean_fn=self._mean)
+        self.ug = user_graph
+        P, d = part.world_size, part.d
+        f0, f1 = part.final_users(rank)
+        self.n_final = f1 - f0
+        u0, u1 = part.rows.users(self.r)
+        self.n_local = u1 - u0
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self._tok_u = torch.empty(0, device=device)  # stand-ins for "the result tables" handed to the inner propagator
+        self._tok_i = torch.empty(0, device=device)
+        if exchange == "p2p":
+            from . import ops
+            self._ops = ops
+            self.buf_u = ops.PeerBuffer(max(part.per, 1) * d * 4, device)
+            self.buf_i = ops.PeerBuffer(part.n_items * d * 4, device)
+            handles = [None] * P
+            if P > 1:
+                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle), group=group)
+            self.peer_u = [self.buf_u.ptr if q == rank else self.buf_u.open_peer(handles[q][0]) for q in range(P)]
+            self.peer_i = [self.buf_i.ptr if q == rank else self.buf_i.open_peer(handles[q][1]) for q in range(P)]
+            self.out_u = self.buf_u.tensor((max(part.per, 1), d))
+            self.out_i = self.buf_i.tensor((part.n_items, d))
+        elif exchange == "collective":
+            self.out_u = torch.empty((max(part.per, 1), d), dtype=torch.float32, device=device)
+            self.out_i = torch.empty((part.n_items, d), dtype=torch.float32, device=device)
+            self.loc_u = torch.empty((self.n_local, part.ds), dtype=torch.float32, device=device)
+            self.loc_i = torch.empty((part.n_items, part.ds), dtype=torch.float32, device=device)
+        else:
+            raise ValueError(f"unknown exchange {exchange!r}")
+        self.comm_bytes_per_hop = part.n_items * part.ds * 4 if part.R > 1 else 0
+
+    # -- hooks handed to the inner propagator: the two result tables are written by the exchange ----------------
+    def _spmm(self, graph, x, y, addends, divisor):
+        if y is not self._tok_u:
+            return self._spmm_fn(graph, x, y, addends, divisor)
+        if self.exchange == "p2p":
+            part = self.part
+            return self._ops.spmm_scatter(graph, x, addends, divisor, part.d, part.cols(self.g)[0], part.per, self.peer_u, self.peer_i)
+        return self._spmm_fn(graph, x, self.loc_u, addends, divisor)
+
+    def _mean(self, addends, out, divisor):
+        if out is not self._tok_i:
+            return self._mean_fn(addends, out, divisor)
+        if self.exchange == "p2p":
+            part = self.part
+            i0, i1 = item_shard(part.n_items, part.R, self.r)  # row-group members hold identical sums: each ships 1/R
+            if i1 > i0:
+                self._ops.layer_mean_scatter([a[i0:i1] for a in addends], divisor, part.d, part.cols(self.g)[0], i0, self.peer_i)
+            return None
+        return self._mean_fn(addends, self.loc_i, divisor)
+
+    def _barrier(self) -> None:
+        if self.part.world_size > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def propagate(self, e0_user_slice_local: torch.Tensor, e0_item_slice: torch.Tensor, single: bool = False):
+        """e0_user_slice_local: rows of this rank's row-group users, columns of its slice (n_local, d/G); e0_item_slice:
+        (n_items, d/G).  Returns (users_emb rows [rank·per, ...) (n_final, d), items_emb (n_items, d))."""
+        part, P = self.part, self.part.world_size
+        if self.exchange == "p2p":
+            self._barrier()  # every rank is done reading the previous result tables
+            if single:
+                raise NotImplementedError("single-layer output is not wired through the p2p exchange")
+            self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self._tok_i, single=False)
+            self._barrier()  # every rank's stores have landed
+            return self.out_u[:self.n_final], self.out_i
+        self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self.loc_i if single else self._tok_i, single=single)
+        ds, ni = part.ds, part.n_items
+        me0, me1 = part.final_users(self.rank)
+
+        def overlap(a0, a1, b0, b1):
+            lo, hi = max(a0, b0), min(a1, b1)
+            return (lo, hi) if hi > lo else (lo, lo)
+
+        u0, u1 = part.rows.users(self.r)
+        send = [overlap(u0, u1, *part.final_users(q)) for q in range(P)]
+        recv = [overlap(*part.rows.users(q % part.R), me0, me1) for q in range(P)]
+        if P > 1:
+            buf = torch.empty((sum(hi - lo for lo, hi in recv), ds), dtype=self.loc_u.dtype, device=self.loc_u.device)
+            dist.all_to_all_single(buf, self.loc_u, output_split_sizes=[hi - lo for lo, hi in recv],
+                                   input_split_sizes=[hi - lo for lo, hi in send], group=self.group)
+            per_i = -(-ni // part.R)
+            i0, i1 = item_shard(ni, part.R, self.r)
+            mine = torch.zeros((per_i, ds), dtype=self.loc_i.dtype, device=self.loc_i.device)
+            mine[:i1 - i0] = self.loc_i[i0:i1]
+            gath = torch.empty((P * per_i, ds), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(gath, mine, group=self.group)
+        else:
+            buf, gath, per_i = self.loc_u, self.loc_i, ni
+        off = 0
+        for q in range(P):
+            gq, rq = part.coords(q)
+            lo, hi = recv[q]
+            if hi > lo:
+                self.out_u[lo - me0:hi - me0, gq * ds:(gq + 1) * ds] = buf[off:off + hi - lo]
+                off += hi - lo
+            j0, j1 = item_shard(ni, part.R, rq)
+            if j1 > j0:
+                self.out_i[j0:j1, gq * ds:(gq + 1) * ds] = gath[q * per_i:q * per_i + (j1 - j0)]
+        return self.out_u[:self.n_final], self.out_i
+
+    def close(self) -> None:
+        if self.exchange == "p2p":
+            self.buf_u.close()
+            self.buf_i.close()
+
+
 def item_shard(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
     per = (n_items + world_size - 1) // world_size
     return min(rank * per, n_items), min((rank + 1) * per, n_items)

@@ -224,6 +224,105 @@ def propagate_host(g: Graph, h_user_w: torch.Tensor, h_item_w: torch.Tensor, h_o
     return h_out
 
 
+class PeerBuffer:
+    """Device memory other ranks can map (CUDA IPC): the row-sharded result tables of the feature-sliced
+    multi-GPU propagation live here so that peers' SpMM epilogues can store into them over NVLink.
+    ``handle`` (64 bytes) is what travels to the other ranks; ``tensor(shape)`` views the memory as fp32."""
+
+    def __init__(self, nbytes: int, device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.nbytes = int(nbytes)
+        ptr = ctypes.c_void_p()
+        hbuf = (ctypes.c_uint8 * 64)()
+        with torch.cuda.device(self.device):
+            check(self.lib.tgcn_peer_alloc(self.nbytes, ctypes.byref(ptr), ctypes.cast(hbuf, ctypes.c_void_p)))
+        self.ptr = int(ptr.value)
+        self.handle = bytes(hbuf)
+        self._opened = []
+
+    def tensor(self, shape) -> torch.Tensor:
+        n = int(np.prod(shape))
+        if n * 4 > self.nbytes:
+            raise _lib.TgcnError("peer buffer too small for the requested view")
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (self.ptr, False), "version": 3}
+        return torch.as_tensor(self, device=self.device).view(*shape)
+
+    def open_peer(self, handle: bytes) -> int:
+        """Map another rank's buffer into this process; returns the device pointer valid here."""
+        ptr = ctypes.c_void_p()
+        hbuf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        with torch.cuda.device(self.device):
+            check(self.lib.tgcn_peer_open(ctypes.cast(hbuf, ctypes.c_void_p), ctypes.byref(ptr)))
+        self._opened.append(int(ptr.value))
+        return int(ptr.value)
+
+    def close(self) -> None:
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self.lib.tgcn_peer_close(p)
+            self._opened = []
+            if self.ptr:
+                self.lib.tgcn_peer_free(self.ptr)
+                self.ptr = 0
+
+
+def spmm_scatter(g: Graph, x: torch.Tensor, addends: Sequence[torch.Tensor], divisor: float, d_full: int, col_off: int,
+                 users_per_rank: int, peer_user_ptrs: Sequence[int], peer_item_ptrs: Sequence[int]) -> None:
+    """One SpMM pass (row-block or whole-graph handle, contiguous operands) whose result rows are stored into the peers'
+    full-width tables by global row id (see tgcn_spmm_scatter)."""
+    _chk(x, torch.float32, "x", 2)
+    ds = x.shape[1]
+    n = len(addends)
+    arr = (ctypes.c_void_p * max(n, 1))(*[_chk(t, torch.float32, "addend", 2).data_ptr() for t in addends])
+    nul = (ctypes.c_void_p * max(n, 1))()
+    np_ = len(peer_user_ptrs)
+    pu = (ctypes.c_void_p * np_)(*peer_user_ptrs)
+    pi = (ctypes.c_void_p * np_)(*peer_item_ptrs)
+    ws = g.workspace(ds, 1)
+    with torch.cuda.device(x.device):
+        check(g.lib.tgcn_spmm_scatter(g.handle, ds, _ptr(x), None, n, arr, nul, float(divisor), int(d_full), int(col_off), np_,
+                                      int(users_per_rank), pu, pi, _ptr(ws), ws.numel(), _stream()))
+
+
+def layer_mean_scatter(addends: Sequence[torch.Tensor], divisor: float, d_full: int, col_off: int, row0: int,
+                       dst_ptrs: Sequence[int]) -> None:
+    """(Σ addends) / divisor over (rows, ds) tables stored at column col_off, rows [row0, row0 + rows) of every
+    destination table (d_full wide; peer-mapped pointers) — see tgcn_layer_mean_scatter."""
+    lib = _lib.load()
+    n = len(addends)
+    rows, ds = addends[0].shape
+    arr = (ctypes.c_void_p * n)(*[_chk(t, torch.float32, "addend", 2).data_ptr() for t in addends])
+    dst = (ctypes.c_void_p * len(dst_ptrs))(*dst_ptrs)
+    with torch.cuda.device(addends[0].device):
+        check(lib.tgcn_layer_mean_scatter(rows, ds, n, arr, float(divisor), int(d_full), int(col_off), int(row0), len(dst_ptrs), dst,
+                                          _stream()))
+
+
+def propagate_sliced(g: Graph, user_slice: torch.Tensor, item_slice: torch.Tensor, n_layers: int, d_full: int, col_off: int,
+                     users_per_rank: int, peer_user_ptrs: Sequence[int], peer_item_ptrs: Sequence[int], single: bool = False,
+                     keep: Optional[torch.Tensor] = None, dropout: float = 0.0) -> None:
+    """representation on one column slice of the tables, the layer mean stored straight into the peers' row-sharded
+    full-width result tables (see tgcn_propagate_sliced).  The caller brackets it with barriers."""
+    _chk(user_slice, torch.float32, "user_slice", 2)
+    _chk(item_slice, torch.float32, "item_slice", 2)
+    ds = user_slice.shape[1]
+    if user_slice.shape[0] != g.n_users or item_slice.shape != (g.n_items, ds):
+        raise _lib.TgcnError("embedding slices do not match the graph")
+    if keep is not None:
+        keep = _keep_u8(keep)
+        if keep.numel() != g.nnz:
+            raise _lib.TgcnError("keep mask must have nnz entries")
+    n = len(peer_user_ptrs)
+    pu = (ctypes.c_void_p * n)(*peer_user_ptrs)
+    pi = (ctypes.c_void_p * n)(*peer_item_ptrs)
+    ws = g.workspace(ds, n_layers)
+    with torch.cuda.device(user_slice.device):
+        check(g.lib.tgcn_propagate_sliced(g.handle, ds, n_layers, int(single), _ptr(user_slice), _ptr(item_slice), _ptr(keep),
+                                          float(dropout), int(d_full), int(col_off), n, int(users_per_rank), pu, pi, _ptr(ws),
+                                          ws.numel(), _stream()))
+
+
 def propagate_bwd(g: Graph, grad_out: torch.Tensor, n_layers: int, single: bool = False,
                   keep: Optional[torch.Tensor] = None, dropout: float = 0.0,
                   grad_in: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:

@@ -388,6 +388,7 @@ class GridPropagator:
         u0, u1 = part.rows.users(self.r)
         self.n_local = u1 - u0
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self._events = [] if os.environ.get("TGCN_GRID_TIMING") else None
         self._tok_u = torch.empty(0, device=device)  # stand-ins for "the result tables" handed to the inner propagator
         self._tok_i = torch.empty(0, device=device)
         if exchange == "p2p":
@@ -412,7 +413,31 @@ class GridPropagator:
         self.comm_bytes_per_hop = part.n_items * part.ds * 4 if part.R > 1 else 0
 
     # -- hooks handed to the inner propagator: the two result tables are written by the exchange ----------------
+    def _timed(self, label, fn):
+        """TGCN_GRID_TIMING=1: CUDA events around every kernel call of a step (read back with timing_report)."""
+        if self._events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self._events.append((label, e0, e1))
+        return out
+
+    def timing_report(self):
+        torch.cuda.synchronize()
+        rep = [(label, round(e0.elapsed_time(e1), 3)) for label, e0, e1 in (self._events or [])]
+        self._events = [] if self._events is not None else None
+        return rep
+
     def _spmm(self, graph, x, y, addends, divisor):
+        label = ("A" if graph is self.ug else "B") + ("_scatter" if y is self._tok_u else "")
+        return self._timed(label, lambda: self._spmm_impl(graph, x, y, addends, divisor))
+
+    def _mean(self, addends, out, divisor):
+        return self._timed("mean" + ("_scatter" if out is self._tok_i else ""), lambda: self._mean_impl(addends, out, divisor))
+
+    def _spmm_impl(self, graph, x, y, addends, divisor):
         if y is not self._tok_u:
             return self._spmm_fn(graph, x, y, addends, divisor)
         if self.exchange == "p2p":
@@ -420,7 +445,7 @@ class GridPropagator:
             return self._ops.spmm_scatter(graph, x, addends, divisor, part.d, part.cols(self.g)[0], part.per, self.peer_u, self.peer_i)
         return self._spmm_fn(graph, x, self.loc_u, addends, divisor)
 
-    def _mean(self, addends, out, divisor):
+    def _mean_impl(self, addends, out, divisor):
         if out is not self._tok_i:
             return self._mean_fn(addends, out, divisor)
         if self.exchange == "p2p":
@@ -440,11 +465,11 @@ class GridPropagator:
         (n_items, d/G).  Returns (users_emb rows [rank·per, ...) (n_final, d), items_emb (n_items, d))."""
         part, P = self.part, self.part.world_size
         if self.exchange == "p2p":
-            self._barrier()  # every rank is done reading the previous result tables
+            self._timed("barrier", self._barrier)  # every rank is done reading the previous result tables
             if single:
                 raise NotImplementedError("single-layer output is not wired through the p2p exchange")
             self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self._tok_i, single=False)
-            self._barrier()  # every rank's stores have landed
+            self._timed("barrier", self._barrier)  # every rank's stores have landed
             return self.out_u[:self.n_final], self.out_i
         self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self.loc_i if single else self._tok_i, single=single)
         ds, ni = part.ds, part.n_items

@@ -11,13 +11,16 @@
 //     128-byte-swizzled K-chunks (32 fp32 = one swizzle row).  Warp 0 = TMA producer, warp 1 = MMA issuer
 //     (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue.
 //   * Accumulators: 2 × BN TMEM columns (double buffered): the epilogue of tile t overlaps the MMAs of tile t+1.
-//   * Epilogue: TMEM lane = user row, so each of the 128 epilogue threads owns one user: it reads its row with
-//     tcgen05.ld (32 columns per instruction), compares every score against its k-th best (one FSETP per score)
-//     tcgen05.ld (32 columns per instruction), builds a branch-free 32-bit hit mask against its k-th best (one
-//     FSETP per score) and only for set bits consults a 128-bit register Bloom filter of the user's train items
-//     (exact binary search in the user row of Â only when the bit is set) and inserts into its private sorted
-//     list, which lives in REGISTERS (shift-insert, ~6 instructions per entry, no memory).  Items arrive in
-//     increasing id order, so a strict '>' keeps the canonical (score desc, id asc) order.
+//   * Epilogue: TMEM lane = user row.  The EW warps of a lane quarter split every tile's COLUMNS, so a user row is
+//     scanned by EW threads, each with a private sorted list in REGISTERS over its share of the items; the lists are
+//     merged (lexicographic insert) once, after the sweep, through the then-idle item ring.  A thread reads 32
+//     scores with tcgen05.ld (the load of the next 32 in flight meanwhile), takes their MAXIMUM (one FMNMX per score,
+//     four independent chains) and compares it with its k-th best; only when that fires — ~k·(1 + ln(n/k)) times per
+//     sweep — does it build the 32-bit hit mask, consult a 128-bit register Bloom filter of the user's train items
+//     (exact binary search in the user row of Â only on a Bloom hit) and shift-insert.  Items arrive in increasing id
+//     order within a thread, so a strict '>' keeps the canonical (score desc, id asc) order.
+//     History (ncu, c2): row-split warps that each rebuilt a full hit mask for 32 rows but owned 16 ran the tensor
+//     pipe at 45 % — 0.37 warp instructions per score, 2 warps per scheduler with a tcgen05.wait::ld stall per group.
 //
 // Roofline: tensor pipe, 3 × 2·K TF32 flops per score (MMA floor 128 cycles per 128×256×8 instruction).
 #include <cuda.h>
@@ -33,7 +36,6 @@ constexpr int TC_BM = 128;
 constexpr int TC_CHUNK = 32;            // fp32 per 128-byte swizzle row
 constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_VSTRIDE = 36;           // floats per row of the hit staging area (32 + pad: conflict-free 128-bit stores)
 
 struct TcArgs {
   int n_rank, K, n_range, item_begin, k;
@@ -123,7 +125,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// v[j] for a run-time j without spilling v to local memory: a 5-level multiplexer of selects (rare path only)
+__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+  const uint32_t d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
+  return __uint_as_float((j & 1) ? d1 : d0);
 }
 
 // ---- per-thread top-k list held in REGISTERS (KL entries, sorted best-first) ------------------------------------
@@ -145,9 +159,23 @@ __device__ __forceinline__ void reg_list_insert(float (&ls)[KL], int (&li)[KL], 
   li[0] = top ? id : li[0];
 }
 
-// BN = item rows per tile, KL = list capacity (>= k), EW = epilogue warps per TMEM lane quarter.  With EW = 2 the two
-// warps of a quarter read the same 32 lanes but own 16 user rows each, which halves the chain of (warp-serialised)
-// list updates — the epilogue's critical path, since hits are rare but divergent.
+// Same for a candidate that may carry a LOWER id than an equal-score entry (merging the lists of the column slices).
+template <int KL>
+__device__ __forceinline__ void reg_list_insert_lex(float (&ls)[KL], int (&li)[KL], float s, int id) {
+#pragma unroll
+  for (int j = KL - 1; j >= 1; --j) {
+    const bool up = ranks_before(s, id, ls[j - 1], li[j - 1]);
+    const bool here = ranks_before(s, id, ls[j], li[j]);
+    ls[j] = up ? ls[j - 1] : (here ? s : ls[j]);
+    li[j] = up ? li[j - 1] : (here ? id : li[j]);
+  }
+  const bool top = ranks_before(s, id, ls[0], li[0]);
+  ls[0] = top ? s : ls[0];
+  li[0] = top ? id : li[0];
+}
+
+// BN = item rows per tile, KL = list capacity (>= k), EW = epilogue warps per TMEM lane quarter: warp `sub` of a quarter
+// scans columns [sub·BN/EW, (sub+1)·BN/EW) of every tile for the quarter's 32 user rows.
 // STREAM = false: the user tile [hi | lo] stays resident in shared memory for the whole sweep (K <= 128).
 // STREAM = true : wide contractions (the LTR score, K = d + 2D + bias chunk): user and item K-chunks travel together
 //                 through the ring, one stage = {U_hi, U_lo, I_hi, I_lo} of one 32-wide K-chunk (12 MMAs per stage).
@@ -162,8 +190,8 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BN * 128 : BN * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
-  float* stage_v = reinterpret_cast<float*>(gen_base + n_a * TC_A_CHUNK_BYTES + a.n_stages * B_STAGE_BYTES);  // [128][36]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_v + TC_BM * TC_VSTRIDE);
+  uint8_t* ring = gen_base + n_a * TC_A_CHUNK_BYTES;  // item ring; reused for the list merge once the sweep is over
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + a.n_stages * B_STAGE_BYTES);
   const uint32_t bar_a_full = smem_u32(bars + 0);
   const uint32_t bar_b_full = smem_u32(bars + 1);                      // [TC_MAX_STAGES]
   const uint32_t bar_b_empty = smem_u32(bars + 1 + TC_MAX_STAGES);     // [TC_MAX_STAGES]
@@ -311,13 +339,15 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ---- epilogue: one thread per user row (EW warps share a lane quarter, 32 / EW rows each) ----
-    const int ew = warp & 3;         // the TMEM lane quarter this warp may read (warp id % 4)
-    const int sub = (warp - 4) >> 2;  // which slice of the quarter's 32 rows this warp owns
+    // ---- epilogue: EW threads per user row, each scanning BN / EW columns of every tile ----
+    constexpr int CW = BN / EW;       // columns per warp and tile
+    constexpr int NG = CW / 32;       // 32-column groups per warp and tile
+    static_assert(NG >= 2 && NG % 2 == 0, "the TMEM loads are double buffered two groups at a time");
+    const int ew = warp & 3;          // the TMEM lane quarter this warp may read (warp id % 4)
+    const int sub = (warp - 4) >> 2;  // which column slice of every tile this warp scans
     const int t = ew * 32 + lane;
     const int m = m0 + t;
-    const bool mine = (lane / (32 / EW)) == sub;
-    const bool valid = mine && m < a.n_rank;
+    const bool valid = m < a.n_rank;
     const int user = valid ? (a.users ? __ldg(a.users + m) : m) : 0;
     int mlo = 0, mhi = 0;
     if (valid && a.mrowptr) {
@@ -349,49 +379,53 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       li[j] = INT_MAX;
     }
     float thr = -INFINITY;
+    // 32 scores of this row: nothing to do unless their maximum beats the row's current k-th best
+    auto scan32 = [&](const uint32_t (&v)[32], int nbase) {
+      float mx[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+      for (int j = 4; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(v[j]));
+      if (!(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) > thr) || !valid) return;
+      // rare and divergent: ~k·(1 + ln(n/k)) candidates per list over the whole sweep
+      uint32_t h4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (__uint_as_float(v[j]) > thr) h4[j & 3] |= 1u << j;
+      uint32_t hits = (h4[0] | h4[1]) | (h4[2] | h4[3]);
+      const int rem = a.n_range - nbase;  // columns past the item range hold zero-filled rows
+      if (rem < 32) hits &= rem > 0 ? (1u << rem) - 1u : 0u;
+      while (hits) {
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const float s = pick32(v, j);
+        if (s > thr) {
+          const int item = a.item_begin + nbase + j;
+          const uint32_t b = (uint32_t)item & 127u;
+          const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
+          const bool maybe = (word >> (b & 31)) & 1u;
+          if (!maybe || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
+            reg_list_insert<KL>(ls, li, s, item);
+            thr = ls[KL - 1];
+          }
+        }
+      }
+    };
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(bar_t_full + 8 * as, aphase);
       tc_fence_after();
-      const int n0 = tile * BN;
+      const int n0 = tile * BN + sub * CW;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + sub * CW;
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
 #pragma unroll 1
-      for (int g = 0; g < BN / 32; ++g) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + g * 32, v);
-        const int nbase = n0 + g * 32;
-        // hit mask: one FSETP + one predicated OR per score against the row's current k-th best
-        uint32_t h4[4] = {0u, 0u, 0u, 0u};  // four independent OR chains instead of one 32-long dependency chain
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (__uint_as_float(v[j]) > thr) h4[j & 3] |= 1u << j;
-        uint32_t hits = (h4[0] | h4[1]) | (h4[2] | h4[3]);
-        const int rem = a.n_range - nbase;  // columns past the item range hold zero-filled rows
-        if (rem < 32) hits &= rem > 0 ? (1u << rem) - 1u : 0u;
-        if (!valid) hits = 0;
-        if (hits) {  // rare and divergent: ~k·(1 + ln(n/k)) candidates per user over the whole sweep
-          // park the 32 scores in this row's private shared-memory slot so a run-time column can be read back
-          float4* sv = reinterpret_cast<float4*>(stage_v + t * TC_VSTRIDE);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            sv[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                __uint_as_float(v[4 * q + 3]));
-          do {
-            const int j = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const float s = stage_v[t * TC_VSTRIDE + j];
-            if (s > thr) {
-              const int item = a.item_begin + nbase + j;
-              const uint32_t b = (uint32_t)item & 127u;
-              const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
-              const bool maybe = (word >> (b & 31)) & 1u;
-              if (!maybe || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
-                reg_list_insert<KL>(ls, li, s, item);
-                thr = ls[KL - 1];
-              }
-            }
-          } while (hits);
-        }
+      for (int g = 0; g < NG; g += 2) {  // group g + 1 is in flight while group g is scanned
+        tmem_wait_ld();
+        tmem_ld32(taddr + (g + 1) * 32, vb);
+        scan32(va, n0 + g * 32);
+        tmem_wait_ld();
+        if (g + 2 < NG) tmem_ld32(taddr + (g + 2) * 32, va);
+        scan32(vb, n0 + (g + 1) * 32);
       }
       tc_fence_before();
       __syncwarp();
@@ -401,7 +435,32 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         aphase ^= 1;
       }
     }
-    if (valid && a.direct) {
+    if constexpr (EW > 1) {
+      // merge the column slices' lists into warp `sub == 0`'s: the sweep is over (the last accumulator was complete, so
+      // every TMA load has landed and every MMA has read its operands) and the item ring is free
+      float* ms = reinterpret_cast<float*>(ring) + (size_t)t * (2 * KL);
+      int* mi = reinterpret_cast<int*>(ms + KL);
+      for (int r = 1; r < EW; ++r) {
+        if (sub == r) {
+#pragma unroll
+          for (int j = 0; j < KL; ++j) {
+            ms[j] = ls[j];
+            mi[j] = li[j];
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EW) : "memory");
+        if (sub == 0) {
+#pragma unroll 1
+          for (int j = 0; j < KL; ++j) {
+            const int id = mi[j];
+            if (id != INT_MAX) reg_list_insert_lex<KL>(ls, li, ms[j], id);
+          }
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EW) : "memory");
+      }
+    }
+    const bool writer = valid && sub == 0;
+    if (writer && a.direct) {
       int real = 0;  // the list is sorted, so sentinels (never-filled slots) come last
 #pragma unroll
       for (int j = 0; j < KL; ++j) real += li[j] != INT_MAX ? 1 : 0;
@@ -419,7 +478,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           a.out_ids[o + j] = id;
           a.out_scores[o + j] = s;
         }
-    } else if (valid) {
+    } else if (writer) {
       const size_t o = ((size_t)blockIdx.y * a.n_rank + m) * a.k;
 #pragma unroll
       for (int j = 0; j < KL; ++j)
@@ -511,7 +570,7 @@ static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream) 
   *stream = Kp > 128;
   *bn = (*stream || Kp > 64) ? 128 : 256;
   const size_t a_bytes = *stream ? 0 : (size_t)(2 * (Kp / TC_CHUNK)) * TC_A_CHUNK_BYTES;
-  const size_t fixed = 1024 /*align slack*/ + a_bytes + (size_t)TC_BM * TC_VSTRIDE * 4 + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
+  const size_t fixed = 1024 /*align slack*/ + a_bytes + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
   const size_t budget = 227 * 1024;
   const size_t stage = *stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)*bn * 128 : (size_t)*bn * 128;
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
@@ -559,6 +618,10 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   bool stream;
   tc_plan(Kp, &bn, &n_stages, &smem, &stream);
   TGCN_REQUIRE(n_stages >= 2, "3xTF32 path does not fit in shared memory for K=%lld", (long long)K);
+  {  // the list merge at the end of a sweep borrows the item ring: 128 rows x (score, id) x list capacity
+    const size_t stage_bytes = stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)bn * 128 : (size_t)bn * 128;
+    TGCN_REQUIRE((size_t)n_stages * stage_bytes >= (size_t)TC_BM * 2 * 40 * 4, "item ring too small for the list merge");
+  }
   const int64_t n_range = item_end - item_begin;
   int n_splits, tps;
   eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);

@@ -346,12 +346,12 @@ def extras_leg(w, graph, dev, flush, torch, batch=2048):
     ds.popularity_users = torch.rand(w["nu"], 1, generator=gen, device=dev)
     ds.popularity_items = torch.rand(w["ni"], 1, generator=gen, device=dev)
     ltr = LTRLinearWPop(make_params(emb_size=w["d"], n_layers=w["L"], k=[20], device=dev, logger=log), ds)
-    n_eval = 8192
+    n_eval = 18944 if os.environ.get("TGCN_LTR_EVAL_USERS") is None else int(os.environ["TGCN_LTR_EVAL_USERS"])
     t = timed_steps(lambda: ltr.predict_device(torch.arange(n_eval, dtype=torch.int32, device=dev)), 2, 1, flush, torch)
     ms = sum(t) / len(t)
     out["ltr_pop"] = {"users_per_s": n_eval / (ms * 1e-3), "ms": ms, "n_users_ranked": n_eval, "text_dim": D, "contraction_width": w["d"] + 2 * D,
                       "tensor_flops_per_s": 3 * 2.0 * (w["d"] + 2 * D) * w["ni"] * n_eval / (ms * 1e-3),
-                      "includes": "propagate, ltr_pack_items/users, tf32_split_kernel x2, eval_topk_tc_kernel<128,20,2,stream> (3xTF32, user and "
+                      "includes": "propagate, ltr_pack_items/users, tf32_split_kernel x2, eval_topk_tc_kernel<256,20,2,stream> (3xTF32, user and "
                                   "item K-chunks streamed together, bias terms folded into one extra K-chunk)"}
     ltr.eval_precision = "fp32"
     t = timed_steps(lambda: ltr.predict_device(torch.arange(n_eval, dtype=torch.int32, device=dev)), 2, 1, flush, torch)
@@ -693,7 +693,7 @@ def main():
         k = args.topk
         if world == 1:
             emb = out
-            n_eval = args.eval_users or (nu if name != "c5" else 16384)
+            n_eval = args.eval_users or (nu if name != "c5" else 2 * 18944)  # 148 SMs x 128-user tiles: whole waves
             users = torch.arange(n_eval, dtype=torch.int32, device=dev)
             h_users = torch.arange(n_eval, dtype=torch.int32).pin_memory()
             h_ids = torch.empty((n_eval, k), dtype=torch.int32).pin_memory()
@@ -709,7 +709,7 @@ def main():
                 h_sc.copy_(sc, non_blocking=True)
         else:
             # headline: user-range sharding (comm-free): every rank ranks a slice of ITS users against all items
-            n_eval = args.eval_users or 16384 * world
+            n_eval = args.eval_users or 18944 * world  # per rank: 148 SMs x 128-user tiles
             n_eval = (n_eval + world - 1) // world * world
             per = n_eval // world
             if args.mg_scheme == "rowblock":

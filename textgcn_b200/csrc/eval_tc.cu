@@ -64,16 +64,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// The suspend-time hint lets the hardware park the waiting thread instead of having it poll: ncu counted 1.06 G of the
+// kernel's 4.5 G issued instructions in the single-thread TMA / MMA wait loops, on the schedulers the epilogue warps need.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -568,10 +570,19 @@ static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 // Shared-memory plan for the tensor-core kernel (Kp = contraction width incl. the bias chunk); 0 stages = does not fit.
 static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream) {
   *stream = Kp > 128;
-  *bn = (*stream || Kp > 64) ? 128 : 256;
   const size_t a_bytes = *stream ? 0 : (size_t)(2 * (Kp / TC_CHUNK)) * TC_A_CHUNK_BYTES;
   const size_t fixed = 1024 /*align slack*/ + a_bytes + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
   const size_t budget = 227 * 1024;
+  // 256-row item tiles whenever three ring stages still fit beside the resident user tile: a 128x128x8 TF32 MMA was
+  // measured at ~117 cycles against 64 ideal (issue overhead per instruction), so wide tiles matter more than ring depth
+  // (c5, d = 128: 357 k -> 544 k users/s, 836 TFLOP/s).  The streamed variant has two 96 KB stages at 256 rows and still gains
+  // (LTR, K = 1600: 875 k -> 1003 k users/s).
+  *bn = 128;
+  if (*stream || (fixed < budget && (budget - fixed) / ((size_t)256 * 128) >= 3)) *bn = 256;
+  {
+    const char* e = getenv("TGCN_EVAL_BN");  // A/B switch
+    if (e && atoi(e) == 128) *bn = 128;
+  }
   const size_t stage = *stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)*bn * 128 : (size_t)*bn * 128;
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
@@ -668,7 +679,11 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
     TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     eval_topk_tc_kernel<BN_, KL_, EW_, ST_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                          \
   } while (0)
-  if (stream) {
+  if (stream && bn == 256) {
+    if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2, true);
+    else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2, true);
+    else TGCN_TC_LAUNCH(256, 64, 1, true);
+  } else if (stream) {
     if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2, true);
     else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2, true);
     else TGCN_TC_LAUNCH(128, 64, 1, true);

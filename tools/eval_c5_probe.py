@@ -9,11 +9,12 @@ graph = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 out = ops.propagate_fwd(graph, w["uw"], w["iw"], L)
 res = {}
-for n in (16384, 65536):
+for n, bn in ((16384, "128"), (18944, "128"), (18944, "256"), (37888, "256")):
+    os.environ["TGCN_EVAL_BN"] = bn
     users = torch.arange(n, dtype=torch.int32, device=dev)
     t = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], 20, users=users), 3, 1, flush, torch)
     ms = sum(t) / len(t)
-    res[f"c5_eval_{n}_users_ms"] = ms
-    res[f"c5_eval_{n}_users_per_s"] = n / ms * 1e3
-    res[f"c5_eval_{n}_tensor_tflops"] = 3 * 2.0 * d * ni * n / (ms * 1e-3) / 1e12
+    res[f"c5_eval_{n}_bn{bn}_ms"] = ms
+    res[f"c5_eval_{n}_bn{bn}_users_per_s"] = n / ms * 1e3
+    res[f"c5_eval_{n}_bn{bn}_tensor_tflops"] = 3 * 2.0 * d * ni * n / (ms * 1e-3) / 1e12
 print(json.dumps(res))

@@ -249,6 +249,17 @@ int tgcn_sample_positives(const tgcn_graph_t* g, int64_t batch, int32_t n_pos, c
 int tgcn_adam_step(int64_t n, float* d_p, const float* d_g, float* d_m, float* d_v, float lr, float beta1,
                    float beta2, float eps, int64_t step, tgcn_stream_t stream);
 
+/* The same two with their per-step scalars in DEVICE memory, so that a whole training step (mask draw, propagate, fused
+ * BPR, backward, Adam) can be captured once in a CUDA graph and replayed (textgcn_b200.train_graph.GraphedTrainStep):
+ * adam_prepare does ++*d_step and writes d_bc = {1 - beta1^step, sqrt(1 - beta2^step)}; adam_step_dev reads d_bc;
+ * counter_inc does ++*d_counter; dropout_mask_dev draws with seed = base_seed + *d_draws · 0xD6E8FEB86659FD93. */
+int tgcn_adam_prepare(int64_t* d_step, float* d_bc, float beta1, float beta2, tgcn_stream_t stream);
+int tgcn_adam_step_dev(int64_t n, float* d_p, const float* d_g, float* d_m, float* d_v, float lr, float beta1, float beta2,
+                       float eps, const float* d_bc, tgcn_stream_t stream);
+int tgcn_counter_inc(uint64_t* d_counter, tgcn_stream_t stream);
+int tgcn_dropout_mask_dev(int64_t nnz, float dropout, uint64_t base_seed, const uint64_t* d_draws, uint8_t* d_keep,
+                          tgcn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

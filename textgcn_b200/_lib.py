@@ -64,6 +64,10 @@ SIGNATURES = {
     "tgcn_dropout_mask": (c_int32, [c_int64, c_float, ctypes.c_uint64, _P, _P]),
     "tgcn_sample_positives": (c_int32, [_P, c_int64, c_int32, _P, ctypes.c_uint64, _P, _P]),
     "tgcn_adam_step": (c_int32, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_int64, _P]),
+    "tgcn_adam_prepare": (c_int32, [_P, _P, c_float, c_float, _P]),
+    "tgcn_adam_step_dev": (c_int32, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P]),
+    "tgcn_counter_inc": (c_int32, [_P, _P]),
+    "tgcn_dropout_mask_dev": (c_int32, [c_int64, c_float, ctypes.c_uint64, _P, _P, _P]),
 }
 
 _lib = None

@@ -146,11 +146,17 @@ __global__ void __launch_bounds__(1024) bpr_finalize_kernel(const float2* __rest
 }
 
 // Dense Adam step, torch.optim.Adam defaults (no amsgrad, no weight decay), float4-vectorised.
+// bc != NULL: the bias corrections come from device memory (written by adam_prepare_kernel), so the launch carries no
+// per-step host scalar and the whole training step can be replayed from a CUDA graph.
 __global__ void __launch_bounds__(256) adam_kernel(int64_t n4, float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v, float lr, float b1, float b2,
-                                                   float eps, float bc1, float bc2_sqrt) {
+                                                   float eps, float bc1, float bc2_sqrt, const float* __restrict__ bc) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
+  if (bc != nullptr) {
+    bc1 = __ldg(bc);
+    bc2_sqrt = __ldg(bc + 1);
+  }
   float4 pi = p[i], mi = m[i], vi = v[i];
   const float4 gi = g[i];
   const float step = lr / bc1;
@@ -163,6 +169,14 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t n4, float4* __restric
   p[i] = pi;
   m[i] = mi;
   v[i] = vi;
+}
+
+// ++*step, then the bias corrections of that step: bc[0] = 1 - b1^step, bc[1] = sqrt(1 - b2^step) (one thread, fp64)
+__global__ void adam_prepare_kernel(long long* __restrict__ step, float* __restrict__ bc, double b1, double b2) {
+  const long long t = *step + 1;
+  *step = t;
+  bc[0] = (float)(1.0 - pow(b1, (double)t));
+  bc[1] = (float)sqrt(1.0 - pow(b2, (double)t));
 }
 
 }  // namespace tgcn
@@ -218,7 +232,27 @@ int tgcn_adam_step(int64_t n, float* d_p, const float* d_g, float* d_m, float* d
   const int threads = 256;
   const int64_t blocks = (n4 + threads - 1) / threads;
   adam_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(n4, (float4*)d_p, (const float4*)d_g, (float4*)d_m, (float4*)d_v,
-                                                                     lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2));
+                                                                     lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), nullptr);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
+
+int tgcn_adam_prepare(int64_t* d_step, float* d_bc, float beta1, float beta2, tgcn_stream_t stream) {
+  TGCN_REQUIRE(d_step && d_bc, "NULL argument");
+  adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)d_step, d_bc, (double)beta1, (double)beta2);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
+
+int tgcn_adam_step_dev(int64_t n, float* d_p, const float* d_g, float* d_m, float* d_v, float lr, float beta1, float beta2,
+                       float eps, const float* d_bc, tgcn_stream_t stream) {
+  TGCN_REQUIRE(n > 0 && n % 4 == 0, "n=%lld must be a positive multiple of 4", (long long)n);
+  TGCN_REQUIRE(d_p && d_g && d_m && d_v && d_bc, "bad argument");
+  const int64_t n4 = n / 4;
+  const int threads = 256;
+  const int64_t blocks = (n4 + threads - 1) / threads;
+  adam_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(n4, (float4*)d_p, (const float4*)d_g, (float4*)d_m, (float4*)d_v,
+                                                                     lr, beta1, beta2, eps, 1.f, 1.f, d_bc);
   TGCN_CHECK_LAUNCH();
   return 0;
 }

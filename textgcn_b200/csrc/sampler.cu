@@ -63,10 +63,13 @@ __global__ void __launch_bounds__(256) sample_bpr_kernel(const SampleArgs a) {
 
 // n2  Bernoulli(1 - p) edge keep-mask drawn on the device (replaces torch.rand(nnz) on the host + H2D, base_model.py:82):
 // one byte per nnz, 16 entries per thread from four 64-bit hashes, written as one 128-bit store.
+// draws != NULL: the per-draw part of the seed comes from a device counter (seed += *draws · 0xD6E8FEB86659FD93), so the
+// launch carries no per-step host scalar (CUDA-graph replay of the training step).
 __global__ void __launch_bounds__(256) dropout_mask_kernel(long long n16, long long nnz, unsigned long long seed, uint32_t thresh,
-                                                           uint8_t* __restrict__ keep) {
+                                                           const unsigned long long* __restrict__ draws, uint8_t* __restrict__ keep) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n16) return;
+  if (draws != nullptr) seed += __ldg(draws) * 0xD6E8FEB86659FD93ULL;
   uint32_t w[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -149,7 +152,32 @@ extern "C" int tgcn_dropout_mask(int64_t nnz, float dropout, uint64_t seed, uint
   const double keep_p = 1.0 - (double)dropout;
   const uint32_t thresh = keep_p >= 1.0 ? 0xffffffffu : (uint32_t)(keep_p * 4294967296.0);
   const long long n16 = (nnz + 15) / 16;
-  dropout_mask_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n16, nnz, (unsigned long long)seed, thresh, d_keep);
+  dropout_mask_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n16, nnz, (unsigned long long)seed, thresh, nullptr, d_keep);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
+
+namespace tgcn {
+__global__ void counter_inc_kernel(unsigned long long* c) { *c += 1ULL; }
+}  // namespace tgcn
+
+extern "C" int tgcn_counter_inc(uint64_t* d_counter, tgcn_stream_t stream) {
+  TGCN_REQUIRE(d_counter != nullptr, "NULL counter");
+  tgcn::counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)d_counter);
+  TGCN_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int tgcn_dropout_mask_dev(int64_t nnz, float dropout, uint64_t base_seed, const uint64_t* d_draws, uint8_t* d_keep,
+                                     tgcn_stream_t stream) {
+  TGCN_REQUIRE(nnz > 0 && d_keep != nullptr && d_draws != nullptr, "bad arguments");
+  TGCN_REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout=%f out of [0,1)", dropout);
+  TGCN_REQUIRE(((uintptr_t)d_keep & 15) == 0, "keep mask must be 16-byte aligned");
+  const double keep_p = 1.0 - (double)dropout;
+  const uint32_t thresh = keep_p >= 1.0 ? 0xffffffffu : (uint32_t)(keep_p * 4294967296.0);
+  const long long n16 = (nnz + 15) / 16;
+  dropout_mask_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n16, nnz, (unsigned long long)base_seed, thresh,
+                                                                                      (const unsigned long long*)d_draws, d_keep);
   TGCN_CHECK_LAUNCH();
   return 0;
 }

@@ -152,8 +152,12 @@ class B200HotPath:
             return None
         nnz = self.graph.nnz
         if self.dropout_rng == "device":  # one kernel, counter-based hash keyed by torch's seed and a per-model draw counter
+            base = (torch.initial_seed() * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+            draws = self.__dict__.get("_b200_dev_draws")
+            if draws is not None:  # CUDA-graph mode (train_graph.GraphedTrainStep): the draw counter lives on the device
+                return ops.dropout_mask_dev(nnz, float(self.dropout), base, draws)
             n = self.__dict__["_b200_mask_draws"] = self.__dict__.get("_b200_mask_draws", 0) + 1
-            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + n * 0xD6E8FEB86659FD93) & (2 ** 64 - 1)
+            seed = (base + n * 0xD6E8FEB86659FD93) & (2 ** 64 - 1)
             return ops.dropout_mask(nnz, float(self.dropout), seed, self.graph.device)
         return (torch.rand(nnz) < (1 - self.dropout)).to(self.graph.device)
 
@@ -307,6 +311,7 @@ class BaseModel(B200HotPath, nn.Module):
         self.dropout_rng = getattr(params, "dropout_rng", "host")
         self.eval_precision = getattr(params, "eval_precision", "auto")
         self.nan_check = getattr(params, "nan_check", "step")
+        self.cuda_graph = getattr(params, "cuda_graph", False)  # replay the training step from one CUDA graph (train_graph.py)
 
     def _copy_dataset_params(self, dataset):
         self.n_users = dataset.n_users
@@ -349,7 +354,13 @@ class BaseModel(B200HotPath, nn.Module):
 
     def fit(self, batches):
         """base_model.py:108-139."""
-        if self.fused_adam:
+        graphed = None
+        if self.cuda_graph and type(self).get_loss is B200HotPath.get_loss:  # fixed-shape BPR steps only (not AdvSampl / LTR)
+            from .optim import FusedAdam
+            from .train_graph import GraphedTrainStep
+            self.optimizer = FusedAdam(self.parameters(), lr=self.lr, capturable=True)
+            graphed = GraphedTrainStep(self, self.optimizer)
+        elif self.fused_adam:
             from .optim import FusedAdam
             self.optimizer = FusedAdam(self.parameters(), lr=self.lr)
         else:
@@ -361,6 +372,11 @@ class BaseModel(B200HotPath, nn.Module):
             epoch_loss = 0
             nan_seen = torch.zeros((), dtype=torch.bool, device=self.device)
             for data in batches:
+                if graphed is not None:
+                    batch_loss = graphed(data)
+                    nan_seen |= batch_loss.isnan()
+                    epoch_loss += batch_loss
+                    continue
                 self.optimizer.zero_grad()
                 batch_loss = self.get_loss(data)
                 if self.nan_check == "step":  # the reference's per-step device sync (base_model.py:123)
@@ -371,6 +387,10 @@ class BaseModel(B200HotPath, nn.Module):
                 batch_loss.backward()
                 self.optimizer.step()
             assert not bool(nan_seen), f"loss is NA at epoch {epoch}"
+            if graphed is not None:  # the graph accumulates [bpr, reg] in place; hand the epoch's sums to the logger
+                sums = graphed.loss_sums.clone()
+                graphed.loss_sums.zero_()
+                self._loss_values["bpr"], self._loss_values["reg"] = sums[0], sums[1]
             if epoch % self.evaluate_every:
                 continue
             self.logger.info(f"Epoch {epoch}: {' '.join([f'{k} = {float(v):.4f}' for k, v in self._loss_values.items()])}")

@@ -177,6 +177,19 @@ def dropout_mask(nnz: int, dropout: float, seed: int, device) -> torch.Tensor:
     return keep
 
 
+def dropout_mask_dev(nnz: int, dropout: float, base_seed: int, draws: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Same draw with the per-draw part of the seed read from the device counter ``draws`` (int64, 1 element), which is
+    incremented first: no per-step host scalar, so the call can be replayed from a CUDA graph."""
+    lib = _lib.load()
+    if draws.dtype != torch.int64 or not draws.is_cuda or draws.numel() != 1:
+        raise _lib.TgcnError("draws must be a 1-element int64 CUDA tensor")
+    keep = torch.empty(nnz, dtype=torch.uint8, device=draws.device) if out is None else out
+    with torch.cuda.device(draws.device):
+        check(lib.tgcn_counter_inc(_ptr(draws), _stream()))
+        check(lib.tgcn_dropout_mask_dev(nnz, float(dropout), base_seed & (2 ** 64 - 1), _ptr(draws), _ptr(keep), _stream()))
+    return keep
+
+
 def _keep_u8(keep: torch.Tensor) -> torch.Tensor:
     if keep.dtype == torch.bool:
         keep = keep.view(torch.uint8)
@@ -476,6 +489,20 @@ def ltr_pack_users(users: Optional[torch.Tensor], users_emb, users_rev, users_de
                                       _ptr(_chk(users_rev, torch.float32, "users_rev")),
                                       _ptr(_chk(users_desc, torch.float32, "users_desc")), _ptr(out), _stream()))
     return out
+
+
+def adam_prepare(step: torch.Tensor, bc: torch.Tensor, beta1: float, beta2: float) -> None:
+    """++step (int64 device counter) and bc = [1 - beta1^step, sqrt(1 - beta2^step)] (2 floats on the device)."""
+    lib = _lib.load()
+    with torch.cuda.device(step.device):
+        check(lib.tgcn_adam_prepare(_ptr(step), _ptr(bc), beta1, beta2, _stream()))
+
+
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, bc: torch.Tensor) -> None:
+    lib = _lib.load()
+    with torch.cuda.device(p.device):
+        check(lib.tgcn_adam_step_dev(p.numel(), _ptr(p), _ptr(_chk(g, torch.float32, "grad")), _ptr(m), _ptr(v), lr, beta1,
+                                     beta2, eps, _ptr(bc), _stream()))
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step) -> None:

@@ -14,12 +14,41 @@ from . import ops
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """``capturable=True`` keeps the step count and the bias corrections in device memory (one tiny kernel per step
+    and parameter group), so ``step()`` issues no per-step host scalar and can be replayed from a CUDA graph; it then
+    only accepts parameters the fused kernel handles (fp32, contiguous, size % 4 == 0)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = capturable
+
+    def _step_capturable(self):
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            dev = params[0].device
+            if "dev_step" not in group:
+                group["dev_step"] = torch.zeros(1, dtype=torch.int64, device=dev)
+                group["dev_bc"] = torch.zeros(2, dtype=torch.float32, device=dev)
+            ops.adam_prepare(group["dev_step"], group["dev_bc"], b1, b2)
+            for p in params:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.numel() % 4 == 0 and p.is_contiguous()):
+                    raise ValueError("FusedAdam(capturable=True) needs fp32 contiguous CUDA parameters with numel % 4 == 0")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ops.adam_step_dev(p, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
+                                  group["dev_bc"])
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if self.capturable:
+            self._step_capturable()
+            return loss
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:

@@ -228,6 +228,41 @@ class BipartitePropagator:
         return out_user_local, out_item
 
 
+class _ResultTables:
+    """The row-sharded result of the sliced / grid schemes: (per, d) user rows + (n_items, d) item table per rank.
+    ``p2p``: the tables live in CUDA-IPC peer memory and ``peer_u`` / ``peer_i`` hold every rank's mapping of every
+    table, so SpMM epilogues can store into them over NVLink; otherwise plain torch tensors."""
+
+    def __init__(self, per: int, n_items: int, d: int, world_size: int, rank: int, device, group, p2p: bool):
+        self.world_size, self.group, self.p2p = world_size, group, p2p
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        rows = max(per, 1)
+        if p2p:
+            from . import ops
+            self.buf_u = ops.PeerBuffer(rows * d * 4, device)
+            self.buf_i = ops.PeerBuffer(n_items * d * 4, device)
+            handles = [None] * world_size
+            if world_size > 1:
+                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle), group=group)
+            self.peer_u = [self.buf_u.ptr if q == rank else self.buf_u.open_peer(handles[q][0]) for q in range(world_size)]
+            self.peer_i = [self.buf_i.ptr if q == rank else self.buf_i.open_peer(handles[q][1]) for q in range(world_size)]
+            self.out_u = self.buf_u.tensor((rows, d))
+            self.out_i = self.buf_i.tensor((n_items, d))
+        else:
+            self.out_u = torch.empty((rows, d), dtype=torch.float32, device=device)
+            self.out_i = torch.empty((n_items, d), dtype=torch.float32, device=device)
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier: returns (on the stream) once every rank's earlier work on its stream is complete."""
+        if self.world_size > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self) -> None:
+        if self.p2p:
+            self.buf_u.close()
+            self.buf_i.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Feature-sliced scheme: every GPU runs all L hops on d/P columns of the tables; ONE exchange, fused into the last pass
 # ---------------------------------------------------------------------------------------------------------
@@ -273,35 +308,20 @@ class SlicedPropagator:
                  exchange: str = "p2p", local_fn: Callable = _default_local_propagate):
         self.part, self.rank, self.graph, self.n_layers, self.group = part, rank, graph, n_layers, group
         self.exchange, self.local_fn = exchange, local_fn
+        if exchange not in ("p2p", "collective"):
+            raise ValueError(f"unknown exchange {exchange!r}")
         P, d, ds = part.world_size, part.d, part.ds
         u0, u1 = part.users(rank)
         self.n_local = u1 - u0
-        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.tables = _ResultTables(part.per, part.n_items, d, P, rank, device, group, p2p=exchange == "p2p")
+        self.out_u, self.out_i = self.tables.out_u, self.tables.out_i
         if exchange == "p2p":
             from . import ops
             self._ops = ops
-            self.buf_u = ops.PeerBuffer(max(part.per, 1) * d * 4, device)
-            self.buf_i = ops.PeerBuffer(part.n_items * d * 4, device)
-            handles = [None] * P
-            if P > 1:
-                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle), group=group)
-            self.peer_u = [self.buf_u.ptr if q == rank else self.buf_u.open_peer(handles[q][0]) for q in range(P)]
-            self.peer_i = [self.buf_i.ptr if q == rank else self.buf_i.open_peer(handles[q][1]) for q in range(P)]
-            self.out_u = self.buf_u.tensor((max(part.per, 1), d))
-            self.out_i = self.buf_i.tensor((part.n_items, d))
-        elif exchange == "collective":
-            self.out_u = torch.empty((max(part.per, 1), d), dtype=torch.float32, device=device)
-            self.out_i = torch.empty((part.n_items, d), dtype=torch.float32, device=device)
-            self.local = torch.empty((part.n_users + part.n_items, ds), dtype=torch.float32, device=device)
         else:
-            raise ValueError(f"unknown exchange {exchange!r}")
+            self.local = torch.empty((part.n_users + part.n_items, ds), dtype=torch.float32, device=device)
         # sent per rank: its column slice of every user row to the owner and of every item row to all peers
         self.comm_bytes_per_step = (part.n_users - self.n_local) * ds * 4 + (P - 1) * part.n_items * ds * 4
-
-    def _barrier(self) -> None:
-        """Stream-ordered barrier: returns (on the stream) once every rank's earlier work on its stream is complete."""
-        if self.part.world_size > 1:
-            dist.all_reduce(self._flag, group=self.group)
 
     def propagate(self, user_slice: torch.Tensor, item_slice: torch.Tensor, single: bool = False):
         """user_slice (n_users, d/P), item_slice (n_items, d/P): this rank's columns of E0.  Returns (users_emb rows of
@@ -309,10 +329,10 @@ class SlicedPropagator:
         part, P = self.part, self.part.world_size
         nu, ni, ds = part.n_users, part.n_items, part.ds
         if self.exchange == "p2p":
-            self._barrier()  # every rank is done reading the previous result tables
+            self.tables.barrier()  # every rank is done reading the previous result tables
             self._ops.propagate_sliced(self.graph, user_slice, item_slice, self.n_layers, part.d, part.cols(self.rank)[0],
-                                       part.per, self.peer_u, self.peer_i, single=single)
-            self._barrier()  # every rank's stores have landed
+                                       part.per, self.tables.peer_u, self.tables.peer_i, single=single)
+            self.tables.barrier()  # every rank's stores have landed
         else:
             loc = self.local_fn(self.graph, user_slice, item_slice, self.n_layers, single, self.local)
             n_my = self.n_local
@@ -329,9 +349,7 @@ class SlicedPropagator:
         return self.out_u[:self.n_local], self.out_i
 
     def close(self) -> None:
-        if self.exchange == "p2p":
-            self.buf_u.close()
-            self.buf_i.close()
+        self.tables.close()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -387,29 +405,19 @@ class GridPropagator:
         self.n_final = f1 - f0
         u0, u1 = part.rows.users(self.r)
         self.n_local = u1 - u0
-        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        if exchange not in ("p2p", "collective"):
+            raise ValueError(f"unknown exchange {exchange!r}")
         self._events = [] if os.environ.get("TGCN_GRID_TIMING") else None
         self._tok_u = torch.empty(0, device=device)  # stand-ins for "the result tables" handed to the inner propagator
         self._tok_i = torch.empty(0, device=device)
+        self.tables = _ResultTables(part.per, part.n_items, d, P, rank, device, group, p2p=exchange == "p2p")
+        self.out_u, self.out_i = self.tables.out_u, self.tables.out_i
         if exchange == "p2p":
             from . import ops
             self._ops = ops
-            self.buf_u = ops.PeerBuffer(max(part.per, 1) * d * 4, device)
-            self.buf_i = ops.PeerBuffer(part.n_items * d * 4, device)
-            handles = [None] * P
-            if P > 1:
-                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle), group=group)
-            self.peer_u = [self.buf_u.ptr if q == rank else self.buf_u.open_peer(handles[q][0]) for q in range(P)]
-            self.peer_i = [self.buf_i.ptr if q == rank else self.buf_i.open_peer(handles[q][1]) for q in range(P)]
-            self.out_u = self.buf_u.tensor((max(part.per, 1), d))
-            self.out_i = self.buf_i.tensor((part.n_items, d))
-        elif exchange == "collective":
-            self.out_u = torch.empty((max(part.per, 1), d), dtype=torch.float32, device=device)
-            self.out_i = torch.empty((part.n_items, d), dtype=torch.float32, device=device)
+        else:
             self.loc_u = torch.empty((self.n_local, part.ds), dtype=torch.float32, device=device)
             self.loc_i = torch.empty((part.n_items, part.ds), dtype=torch.float32, device=device)
-        else:
-            raise ValueError(f"unknown exchange {exchange!r}")
         self.comm_bytes_per_hop = part.n_items * part.ds * 4 if part.R > 1 else 0
 
     # -- hooks handed to the inner propagator: the two result tables are written by the exchange ----------------
@@ -442,7 +450,8 @@ class GridPropagator:
             return self._spmm_fn(graph, x, y, addends, divisor)
         if self.exchange == "p2p":
             part = self.part
-            return self._ops.spmm_scatter(graph, x, addends, divisor, part.d, part.cols(self.g)[0], part.per, self.peer_u, self.peer_i)
+            return self._ops.spmm_scatter(graph, x, addends, divisor, part.d, part.cols(self.g)[0], part.per, self.tables.peer_u,
+                                          self.tables.peer_i)
         return self._spmm_fn(graph, x, self.loc_u, addends, divisor)
 
     def _mean_impl(self, addends, out, divisor):
@@ -452,24 +461,20 @@ class GridPropagator:
             part = self.part
             i0, i1 = item_shard(part.n_items, part.R, self.r)  # row-group members hold identical sums: each ships 1/R
             if i1 > i0:
-                self._ops.layer_mean_scatter([a[i0:i1] for a in addends], divisor, part.d, part.cols(self.g)[0], i0, self.peer_i)
+                self._ops.layer_mean_scatter([a[i0:i1] for a in addends], divisor, part.d, part.cols(self.g)[0], i0, self.tables.peer_i)
             return None
         return self._mean_fn(addends, self.loc_i, divisor)
-
-    def _barrier(self) -> None:
-        if self.part.world_size > 1:
-            dist.all_reduce(self._flag, group=self.group)
 
     def propagate(self, e0_user_slice_local: torch.Tensor, e0_item_slice: torch.Tensor, single: bool = False):
         """e0_user_slice_local: rows of this rank's row-group users, columns of its slice (n_local, d/G); e0_item_slice:
         (n_items, d/G).  Returns (users_emb rows [rank·per, ...) (n_final, d), items_emb (n_items, d))."""
         part, P = self.part, self.part.world_size
         if self.exchange == "p2p":
-            self._timed("barrier", self._barrier)  # every rank is done reading the previous result tables
+            self._timed("barrier", self.tables.barrier)  # every rank is done reading the previous result tables
             if single:
                 raise NotImplementedError("single-layer output is not wired through the p2p exchange")
             self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self._tok_i, single=False)
-            self._timed("barrier", self._barrier)  # every rank's stores have landed
+            self._timed("barrier", self.tables.barrier)  # every rank's stores have landed
             return self.out_u[:self.n_final], self.out_i
         self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self.loc_i if single else self._tok_i, single=single)
         ds, ni = part.ds, part.n_items
@@ -507,9 +512,7 @@ class GridPropagator:
         return self.out_u[:self.n_final], self.out_i
 
     def close(self) -> None:
-        if self.exchange == "p2p":
-            self.buf_u.close()
-            self.buf_i.close()
+        self.tables.close()
 
 
 def item_shard(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:

@@ -201,3 +201,30 @@ def test_partition_relabel_roundtrip():
         assert part.starts[p] <= c < part.starts[p + 1]
         assert int(rel[c]) == p * part.max_rows + (c - part.starts[p])
     assert tdist.item_shard(10, 4, 3) == (9, 10) and tdist.item_shard(10, 4, 0) == (0, 3)
+
+
+def test_grid_and_slice_partition_geometry():
+    """Pure host logic: every user / column / item row has exactly one owner and the ranks of a row group are contiguous."""
+    from textgcn_b200 import dist as tdist
+    rowptr = torch.cumsum(torch.tensor([0] + [3, 1, 7, 2, 2, 9, 1, 4, 5, 1] + [4] * 7), 0).to(torch.int32)  # 10 users, 7 items
+    nu, ni, d = 10, 7, 32
+    for G, R in ((1, 4), (2, 2), (4, 1), (2, 4), (8, 1)):
+        gp = tdist.GridPartition(rowptr, nu, ni, d, G, R)
+        assert gp.world_size == G * R and gp.ds * G == d
+        assert sorted(r for g in range(G) for r in gp.row_group_ranks(g)) == list(range(G * R))
+        cover_users, cover_final = [], []
+        for rank in range(G * R):
+            g, r = gp.coords(rank)
+            assert rank == g * R + r and gp.cols(g) == (g * gp.ds, (g + 1) * gp.ds)
+            cover_final += list(range(*gp.final_users(rank)))
+            if g == 0:
+                cover_users += list(range(*gp.rows.users(r)))
+        assert cover_users == list(range(nu)) and cover_final == list(range(nu))
+        shares = [tdist.item_shard(ni, R, r) for r in range(R)]
+        assert [i for a, b in shares for i in range(a, b)] == list(range(ni))
+    fp = tdist.FeatureSlicePartition(nu, ni, d, 4)
+    assert [u for q in range(4) for u in range(*fp.users(q))] == list(range(nu)) and fp.cols(3) == (24, 32)
+    with pytest.raises(ValueError):
+        tdist.FeatureSlicePartition(nu, ni, 20, 4)
+    with pytest.raises(ValueError):
+        tdist.GridPartition(rowptr, nu, ni, 20, 2, 2)

@@ -13,7 +13,6 @@ from textgcn_b200.dist import FeatureSlicePartition  # noqa: E402
 
 dev = torch.device("cuda:0")
 res = {}
-os.environ["TGCN_SLICE_KERNEL"] = "0"
 for name in ("c2", "c5"):
     w = build_workload(name, dev)
     nu, ni, d, L, nnz = w["nu"], w["ni"], w["d"], w["L"], w["nnz"]

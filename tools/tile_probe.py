@@ -44,7 +44,6 @@ for ds in (16,):
     xi = torch.randn(ni, ds, generator=gen, device=dev)
     x = torch.cat([xu, xi])
     y_ref = torch.empty((n, ds), device=dev)
-    os.environ["TGCN_SLICE_KERNEL"] = "0"
     t = timed_steps(lambda: ops.spmm(graph, x, out=y_ref), 3, 1, flush, torch)
     res[f"ds{ds}_untiled_ms"] = round(sum(t) / len(t), 3)
     print(res, file=sys.stderr, flush=True)

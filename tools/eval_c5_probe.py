@@ -9,7 +9,10 @@ graph = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 out = ops.propagate_fwd(graph, w["uw"], w["iw"], L)
 res = {}
-for n, bn in ((16384, "128"), (18944, "128"), (18944, "256"), (37888, "256")):
+CASES = ((16384, "128"), (18944, "128"), (18944, "256"), (37888, "256"))
+if os.environ.get("TGCN_PROBE_ONLY_FINAL"):  # one case, for an ncu capture of the shipped configuration
+    CASES = ((18944, "256"),)
+for n, bn in CASES:
     os.environ["TGCN_EVAL_BN"] = bn
     users = torch.arange(n, dtype=torch.int32, device=dev)
     t = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], 20, users=users), 3, 1, flush, torch)

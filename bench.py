@@ -2,7 +2,7 @@
 """Benchmark of the LightGCN hot path (BASELINE.json metric: propagation edges/s + eval users/s, top-k@20).
 
     python bench.py --gpus N --steps K --warmup W            # ours (N>1: launched by torch.distributed.run)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own BaseModel on the host cores, rank 0 only
 
 Workload.  BASELINE.json quotes the metric as a 1/2/4/8-GPU series, and the only config that names that series is
 configs[4] — the 200M-edge graph (10M users, 2M items, emb 128, 4 layers), which also fits one GPU — so EVERY N runs
@@ -20,7 +20,7 @@ A "step" is one pass of the hot path over the whole graph: ``representation`` = 
           Eval: user-range sharding (comm-free) and the item-range variant with a cross-GPU top-k merge.
 Between timed iterations L2 is flushed (a 256 MiB write); timing is CUDA events on the launching stream, max over
 ranks.  The JSON line also carries ``roofline`` (dominant kernel: spmm_group_kernel, HBM bound), ``cpu_baseline``
-(oracle port on the host cores, N = 1 only), ``torch_cuda_reference`` (the reference's torch.sparse / matmul / topk ops on
+(the reference's own BaseModel on the host cores, N = 1 only), ``torch_cuda_reference`` (the reference's torch.sparse / matmul / topk ops on
 the same GPU), ``eval`` (users/s) and ``clocks``.
 """
 from __future__ import annotations
@@ -34,6 +34,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# c5 eval leg: 8 x 148 SMs x 128-user tiles = 151 552 of the 10M users, the same at every N (whole waves of CTAs at N = 1..8)
+EVAL_USERS_C5 = 8 * 18944
+TF32_DENSE_PEAK_TFLOPS = 1125.0  # B200 nominal dense TF32 (half of the 2.25 PFLOP/s bf16 figure); MEASURED_PEAKS.json has no TF32 entry
 
 METRIC = "propagation edges/s (directed nnz x layers per second; eval users/s top-k@20 in `eval`)"
 
@@ -55,7 +59,6 @@ def parse():
     ap.add_argument("--no-torch-ref", action="store_true", help="skip the torch.sparse-on-CUDA comparator")
     ap.add_argument("--no-extras", action="store_true", help="skip the adv_sampling / LTR legs (BASELINE.json configs[2], [3])")
     ap.add_argument("--topk", type=int, default=20)
-    ap.add_argument("--no-l2-hints", action="store_true", help="disable the L2 cache-policy hints of the SpMM (A/B comparison)")
     ap.add_argument("--ar-chunks", type=int, default=1, help="bipartite scheme: split the item-table all-reduce into this many chunks")
     ap.add_argument("--mg-scheme", default="grid", choices=["grid", "bipartite", "rowblock"],
                     help="multi-GPU propagation: G feature slices x R user partitions with a peer-memory result exchange (grid), "
@@ -240,20 +243,65 @@ def torch_cuda_reference(w, dev, flush, torch, topk, n_eval=8192):
     emb = representation()
     ue, ie = emb[:nu], emb[nu:]
     n_eval = min(n_eval, nu)
+    kept = []
 
     def predict():
+        kept.clear()
         for s0 in range(0, n_eval, 2048):
             users = torch.arange(s0, min(s0 + 2048, n_eval), device=dev)
             scores = ue[users] @ ie.T
             lo, hi = int(rowptr[s0]), int(rowptr[min(s0 + 2048, n_eval)])
             rows = torch.repeat_interleave(torch.arange(users.numel(), device=dev), counts[s0:s0 + users.numel()])
             scores[rows, col[lo:hi].to(torch.int64) - nu] = float("-inf")
-            torch.topk(scores, topk, dim=1)
+            kept.append(torch.topk(scores, topk, dim=1))
 
     te = timed_steps(predict, 2, 1, flush, torch)
     ems = sum(te) / len(te)
-    return {"representation_ms": ms, "edges_per_s": nnz * L / (ms * 1e-3), "eval_users_per_s": n_eval / (ems * 1e-3),
-            "n_users_ranked": n_eval, "ops": "torch.sparse.mm (cuSPARSE) x L + stack/mean; matmul (cuBLAS) + index_put + topk, device-side mask"}
+    res = {"representation_ms": ms, "edges_per_s": nnz * L / (ms * 1e-3), "eval_users_per_s": n_eval / (ems * 1e-3),
+           "n_users_ranked": n_eval, "ops": "torch.sparse.mm (cuSPARSE) x L + stack/mean; matmul (cuBLAS) + index_put + topk, device-side mask"}
+    return res, emb, torch.cat([t.indices for t in kept]), torch.cat([t.values for t in kept])
+
+
+def eval_roofline(tensor_flops_per_gpu, ms):
+    """Tensor-pipe roofline of the fused eval call on one GPU: 3 TF32 MMAs per product (3xTF32), against the nominal dense TF32
+    peak and against half the MEASURED dense bf16 rate (MEASURED_PEAKS.json; cuBLAS 8192^3, the only measured tensor figure)."""
+    ach = tensor_flops_per_gpu / (ms * 1e-3) / 1e12
+    half_bf16 = None
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            half_bf16 = float(json.load(f).get("bf16_tflops", 0)) / 2 or None
+    return {"bound": "tensor", "achieved": ach, "peak": TF32_DENSE_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / TF32_DENSE_PEAK_TFLOPS,
+            "peak_source": "nominal dense TF32 (2.25 PFLOP/s bf16 / 2)", "frac_of_half_measured_bf16": (ach / half_bf16) if half_bf16 else None,
+            "per_gpu": True, "traffic": None,
+            "note": "achieved = 3 x 2 x K x n_items x n_users TF32 flops / CUDA-event time of the whole call (tf32_split_kernel x2 + "
+                    "eval_topk_tc_kernel [+ topk_merge_kernel]), per GPU"}
+
+
+def norm_rel_err(a, b, torch, chunk=1 << 22):
+    """max |a - b| / max |b| over (n, d) device tables, in row chunks (no table-sized temporaries)."""
+    num = den = 0.0
+    for s0 in range(0, a.shape[0], chunk):
+        x, y = a[s0:s0 + chunk], b[s0:s0 + chunk]
+        num = max(num, float((x - y).abs().max()))
+        den = max(den, float(y.abs().max()))
+    return num / max(den, 1e-30)
+
+
+def compare_topk(ids, sc, ref_ids, ref_sc, torch, rtol=1e-5, atol=1e-6):
+    """Tie-aware comparison of our (n, k) table with torch.topk's on the same rows: the reference rows are first put in
+    the canonical order (score desc, id asc; torch.topk's tie order is unspecified); a row is `exact` when
+    the id lists agree, `tied` when they differ only where the position-wise scores agree within rtol/atol (fp32
+    summation-order near-ties), else `bad`."""
+    o = torch.sort(ref_ids, dim=1, stable=True).indices
+    ref_ids, ref_sc = torch.gather(ref_ids, 1, o), torch.gather(ref_sc, 1, o)
+    o = torch.sort(ref_sc, dim=1, descending=True, stable=True).indices
+    ref_ids, ref_sc = torch.gather(ref_ids, 1, o), torch.gather(ref_sc, 1, o)
+    same = (ids.to(torch.int64) == ref_ids).all(1)
+    close = ((sc - ref_sc).abs() <= atol + rtol * ref_sc.abs()) | (torch.isinf(sc) & torch.isinf(ref_sc))
+    tied = ~same & close.all(1)
+    return {"topk_rows": int(ids.shape[0]), "topk_exact": int(same.sum()), "topk_tied": int(tied.sum()),
+            "topk_bad": int((~same & ~close.all(1)).sum())}
 
 
 def c2_leg(args, dev, flush, torch, hbm_peak):
@@ -288,7 +336,7 @@ def c2_leg(args, dev, flush, torch, hbm_peak):
         te = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], k, users=users), args.eval_steps, 1, flush, torch)
         ems = sum(te) / len(te)
         res["eval"] = {"users_per_s": nu / (ems * 1e-3), "ms": ems, "k": k, "n_users_ranked": nu,
-                       "tensor_flops_per_s": 3 * 2.0 * d * ni * nu / (ems * 1e-3)}
+                       "tensor_flops_per_s": 3 * 2.0 * d * ni * nu / (ems * 1e-3), "roofline": eval_roofline(3 * 2.0 * d * ni * nu, ems)}
         n_f = min(nu, 32768)
         tf = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], k, users=users[:n_f].contiguous(), precision="fp32"),
                          1, 1, flush, torch)
@@ -305,11 +353,28 @@ def c2_leg(args, dev, flush, torch, hbm_peak):
             res["configs"] = {"error": str(exc)[:300]}
     if not args.no_torch_ref:
         try:
-            res["torch_cuda_reference"] = torch_cuda_reference(w, dev, flush, torch, k)
+            res["torch_cuda_reference"], ref_emb, ref_ids, ref_sc = torch_cuda_reference(w, dev, flush, torch, k)
+            res["parity"] = parity_vs_torch(ops, graph, out, nu, k, ref_emb, ref_ids, ref_sc, torch)
+            del ref_emb, ref_ids, ref_sc
         except Exception as exc:
             res["torch_cuda_reference"] = {"error": str(exc)[:300]}
     if not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(w, k)
+    return res
+
+
+PARITY_TOL = 1e-5  # north_star: propagated embeddings and scores within 1e-5 relative (norm-wise)
+
+
+def parity_vs_torch(ops, graph, out, nu, k, ref_emb, ref_ids, ref_sc, torch):
+    """Our result against the reference's own ops on the same GPU in the same run: `out` vs torch.sparse's representation
+    (norm-wise), the fused top-k vs matmul + index_put + topk on the same users (tie-aware)."""
+    n_ref = ref_ids.shape[0]
+    users = torch.arange(n_ref, dtype=torch.int32, device=out.device)
+    ids, sc = ops.eval_topk(graph, out[:nu], out[nu:], k, users=users)
+    res = {"prop_rel_err": norm_rel_err(out, ref_emb, torch), "tolerance": PARITY_TOL}
+    res.update(compare_topk(ids, sc, ref_ids, ref_sc, torch))
+    res["ok"] = bool(res["prop_rel_err"] <= PARITY_TOL and res["topk_bad"] == 0)
     return res
 
 
@@ -375,103 +440,105 @@ def extras_leg(w, graph, dev, flush, torch, batch=2048):
     return out
 
 
-def cpu_row_block(w, torch, max_nnz=8_000_000):
-    """Bounded CPU sample of a workload: the leading row block of Â holding <= max_nnz non-zeros (the whole graph at c2)."""
-    n = w["nu"] + w["ni"]
-    rowptr = w["rowptr"].cpu().to(torch.int64)
-    rows = n if w["nnz"] <= max_nnz else int(torch.searchsorted(rowptr, torch.tensor(max_nnz)).item())
-    nnz_s = int(rowptr[rows])
-    row = torch.repeat_interleave(torch.arange(rows), rowptr[1:rows + 1] - rowptr[:rows])
-    block = torch.sparse_coo_tensor(torch.stack([row, w["col"][:nnz_s].cpu().to(torch.int64)]), w["val"][:nnz_s].cpu(),
-                                    (rows, n)).coalesce()
-    return block, rows, nnz_s, rows == n, rowptr
+def reference_sample(w, torch, max_user_nnz=8_000_000):
+    """Bounded CPU sample of a workload for the reference's own BaseModel: the sub-matrix of Â induced by the first U_s
+    users and ALL items — their user rows AND the matching entries of every item row, so the long item rows are timed
+    too — with U_s the largest prefix whose user rows hold <= max_user_nnz non-zeros (the whole graph at c2).  Values are
+    Â's own (same work per non-zero).  Returns CPU numpy CSR arrays with columns renumbered to the sample."""
+    nu, ni = w["nu"], w["ni"]
+    rowptr = w["rowptr"].to(torch.int64)
+    full = int(rowptr[nu]) <= max_user_nnz
+    us = nu if full else int(torch.searchsorted(rowptr[:nu + 1].contiguous(), torch.tensor(max_user_nnz, device=rowptr.device), right=True)) - 1
+    n_u = int(rowptr[us])
+    lo = int(rowptr[nu])
+    icol, ival = w["col"][lo:], w["val"][lo:]
+    keep = icol < us
+    counts = rowptr[nu + 1:] - rowptr[nu:-1]
+    rows = torch.repeat_interleave(torch.arange(ni, device=rowptr.device), counts)[keep]
+    ip = torch.zeros(ni + 1, dtype=torch.int64, device=rowptr.device)
+    ip[1:] = torch.cumsum(torch.bincount(rows, minlength=ni), 0)
+    rp = torch.cat([rowptr[:us + 1], n_u + ip[1:]])
+    col = torch.cat([w["col"][:n_u].to(torch.int64) - nu + us, icol[keep].to(torch.int64)])
+    val = torch.cat([w["val"][:n_u], ival[keep]])
+    return dict(n_users=us, n_items=ni, full=full, nnz=int(col.numel()), rowptr=rp.cpu().numpy(), col=col.cpu().numpy(),
+                val=val.cpu().numpy(), user_w=w["uw"][:us].cpu(), item_w=w["iw"].cpu())
 
 
-def cpu_baseline(w, topk, n_predict=2048):
-    """The reference's CPU path (oracle port: torch.sparse.mm x L + mean; matmul + mask + topk) on the host cores, on a
-    bounded sample: the whole graph when it has <= 8M non-zeros, else a leading row block of Â (same work per non-zero)."""
+def reference_cpu_run(w, topk, steps, warmup, n_predict, budget_s=150.0):
+    """The reference's CPU path on the box's host cores: its own ``BaseModel`` (unmodified, /root/reference or the copy in
+    baseline/_ref) where importable (kind "reference"), else the restated op sequence of oracle/lightgcn_oracle.py (kind
+    "port").  ``representation`` timed `steps` times after `warmup` calls; ``predict`` on the first n_predict users once."""
     import numpy as np
     import torch
     from oracle import lightgcn_oracle as O
+    from oracle import reference_cpu as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    block, rows, nnz_s, full, rowptr = cpu_row_block(w, torch)
-    uw, iw = w["uw"].cpu(), w["iw"].cpu()
-    e0 = torch.cat([uw, iw])
-    best = float("inf")
-    for _ in range(3):
+    smp = reference_sample(w, torch)
+    L, nnz_s = w["L"], smp["nnz"]
+    what = (f"{'full graph' if smp['full'] else 'sub-matrix of Â induced by the first ' + str(smp['n_users']) + ' users and all items'} of "
+            f"{w['name']}: {smp['n_users'] + smp['n_items']} rows, {nnz_s} nnz (user rows and item rows), emb {w['d']}, {L} layers")
+    n_predict = min(n_predict, smp["n_users"])
+    users = np.arange(n_predict)
+    if R.reference_root() is not None:
+        model = R.build_model(smp["n_users"], smp["n_items"], smp["rowptr"], smp["col"], smp["val"], smp["user_w"], smp["item_w"], L,
+                              [topk], batch_size=2048)
+        times = R.time_representation(model, steps, warmup, budget_s)
+        t_pred, t_rep, _ = R.time_predict(model, users)
+        kind = "reference"
+        how = (f"the reference's own BaseModel.representation (base_model.py:93-106), unmodified, device='cpu', {len(times)} timed calls "
+               f"after {warmup} warm-up; BaseModel.predict (:235-276) on {n_predict} users x {smp['n_items']} items = {t_pred * 1e3:.0f} ms "
+               f"including its own representation call ({t_rep * 1e3:.0f} ms)")
+        pred_only = max(t_pred - t_rep, 1e-9)
+    else:
+        row = np.repeat(np.arange(len(smp["rowptr"]) - 1), np.diff(smp["rowptr"]))
+        norm = O.sparse_tensor(row, smp["col"], smp["val"], len(smp["rowptr"]) - 1)
+        times = []
+        for it in range(warmup + steps):
+            t = time.perf_counter()
+            ue, ie = O.propagate(norm, smp["user_w"], smp["item_w"], L)
+            if it >= warmup:
+                times.append(time.perf_counter() - t)
+        ucol = smp["col"][:smp["rowptr"][smp["n_users"]]] - smp["n_users"]
+        lists = np.split(ucol, smp["rowptr"][1:smp["n_users"]])
         t = time.perf_counter()
-        if full:
-            ue, ie = O.propagate(block, uw, iw, w["L"])
-        else:
-            outs = [torch.sparse.mm(block, e0) for _ in range(w["L"])]
-            torch.mean(torch.stack([e0[:rows]] + outs), dim=0)
-            ue, ie = uw, iw  # any fp32 tables of the right shape time the same in predict
-        best = min(best, time.perf_counter() - t)
-    if not full:
-        n_predict = min(n_predict, 256)
-    users = np.arange(min(n_predict, w["nu"]))
-    col = w["col"][:int(rowptr[len(users)])].cpu().numpy().astype(np.int64) - w["nu"]
-    rp = rowptr.numpy()
-    train_lists = [col[rp[u]:rp[u + 1]] for u in users]
-    t = time.perf_counter()
-    O.predict_topk_torch(ue, ie, users, train_lists, topk)
-    t_pred = time.perf_counter() - t
-    res = {"value": nnz_s * w["L"] / best, "unit": "edges/s", "cores": cores, "kind": "port",
-           "sample": f"{'full' if full else 'leading row block of'} {w['name']}: {rows} rows, {nnz_s} nnz, {w['L']} x torch.sparse.mm + "
-                     f"mean, best of 3 = {best * 1e3:.1f} ms; predict on {len(users)} users x {w['ni']} items = {t_pred * 1e3:.1f} ms",
-           "eval_users_per_s": len(users) / t_pred, "ms_per_step": best * 1e3}
-    if full:
-        batch = make_batch(w, 2048, "cpu" if not w["rowptr"].is_cuda else w["rowptr"].device, torch).cpu()
-        keep = torch.rand(block._nnz()) < 0.6
-        t = time.perf_counter()
-        O.train_step_loss_and_grads(block, uw, iw, w["L"], batch, 1e-4, keep_mask=keep, dropout=0.4)
-        res["train_ms_per_step"] = (time.perf_counter() - t) * 1e3
+        O.predict_topk_torch(ue, ie, users, lists, topk)
+        pred_only = time.perf_counter() - t
+        kind = "port"
+        how = f"oracle port (reference not importable): torch.sparse.mm x L + mean, {len(times)} timed calls; predict on {n_predict} users"
+    mean_s = sum(times) / len(times)
+    return {"value": nnz_s * L / mean_s, "unit": "edges/s", "cores": cores, "kind": kind, "sample": what + "; " + how,
+            "ms_per_step": mean_s * 1e3, "best_ms": min(times) * 1e3, "steps": len(times), "warmup": warmup,
+            "eval_users_per_s": n_predict / pred_only, "eval_users_per_s_incl_representation": n_predict / (pred_only + mean_s),
+            "sample_nnz": nnz_s, "workload_nnz": w["nnz"]}
+
+
+def cpu_baseline(w, topk):
+    """cpu_baseline leg of our arm (N = 1, rank 0): the reference's CPU path on a bounded sample, best of 3."""
+    res = reference_cpu_run(w, topk, steps=3, warmup=1, n_predict=8192 if w["nnz"] <= 16_000_000 else 2048, budget_s=60.0)
+    res["value"] = res["sample_nnz"] * w["L"] / (res["best_ms"] * 1e-3)   # BASELINE.md step 4: best of 3
     return res
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads, on a
-    bounded sample of OUR arm's workload (same config / metric / unit)."""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, on a bounded sample of OUR
+    arm's workload (same config / metric / unit; throughput is per non-zero, so the sample and the full graph compare)."""
     if rank != 0:
         return
     import torch
     name = args.workload if args.workload != "auto" else "c5"
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    from oracle import lightgcn_oracle as O
     w = build_workload(name, dev)
-    block, rows, nnz_s, full, _ = cpu_row_block(w, torch)
-    uw, iw = w["uw"].cpu(), w["iw"].cpu()
-    e0 = torch.cat([uw, iw])
-
-    def step():
-        if full:
-            return O.propagate(block, uw, iw, w["L"])
-        outs = [torch.sparse.mm(block, e0) for _ in range(w["L"])]  # L row-block SpMMs (same work per layer)
-        return torch.mean(torch.stack([e0[:rows]] + outs), dim=0)
-
-    for _ in range(min(args.warmup, 2)):
-        step()
-    times = []
-    budget = time.perf_counter() + 150
-    for _ in range(args.steps):
-        t = time.perf_counter()
-        step()
-        times.append(time.perf_counter() - t)
-        if time.perf_counter() > budget:
-            break
-    ms = 1e3 * sum(times) / len(times)
-    value = nnz_s * w["L"] / (ms * 1e-3)
-    sample = (f"{'full' if full else 'leading row block of'} {name}: {rows} rows, {nnz_s} nnz, {w['L']} layers, "
-              f"{len(times)} steps of torch.sparse.mm on {cores} threads")
+    res = reference_cpu_run(w, args.topk, steps=args.steps, warmup=args.warmup, n_predict=8192 if name != "c5" else 2048)
+    value = res["value"]
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus, "steps": len(times),
-        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": args.gpus, "steps": res["steps"],
+        "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "n_users": w["nu"], "n_items": w["ni"], "nnz": w["nnz"], "emb": w["d"], "layers": w["L"]},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "eval": {"users_per_s": res["eval_users_per_s"], "k": args.topk,
+                 "users_per_s_incl_representation": res["eval_users_per_s_incl_representation"]},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -510,8 +577,6 @@ def main():
     extra = {}
     if world == 1:
         graph = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
-        if args.no_l2_hints:
-            graph.set_hot_rows(-1)
         out = torch.empty((n, d), dtype=torch.float32, device=dev)
 
         def step():
@@ -607,7 +672,6 @@ def main():
         u0, u1 = part.users(rank)
         ugraph = ops.Graph(nu, ni, *part.user_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=u0, block=True)
         ugraph.set_mask_col_offset(0)
-        ugraph.set_hot_rows(u1 - u0)  # every row of this block gathers from the replicated item table: keep it in L2
         igraph = ops.Graph(nu, ni, *part.item_block(rank, w["rowptr"], w["col"], w["val"]), row_begin=nu, block=True)
         chunks = None
         if args.ar_chunks > 1:  # chunked item rows: each chunk's all-reduce starts as soon as its SpMM is enqueued
@@ -709,7 +773,7 @@ def main():
         k = args.topk
         if world == 1:
             emb = out
-            n_eval = args.eval_users or (nu if name != "c5" else 2 * 18944)  # 148 SMs x 128-user tiles: whole waves
+            n_eval = args.eval_users or (nu if name != "c5" else EVAL_USERS_C5)
             users = torch.arange(n_eval, dtype=torch.int32, device=dev)
             h_users = torch.arange(n_eval, dtype=torch.int32).pin_memory()
             h_ids = torch.empty((n_eval, k), dtype=torch.int32).pin_memory()
@@ -725,7 +789,7 @@ def main():
                 h_sc.copy_(sc, non_blocking=True)
         else:
             # headline: user-range sharding (comm-free): every rank ranks a slice of ITS users against all items
-            n_eval = args.eval_users or 18944 * world  # per rank: 148 SMs x 128-user tiles
+            n_eval = args.eval_users or (nu if name != "c5" else EVAL_USERS_C5)   # the SAME user count at every N: strong scaling
             n_eval = (n_eval + world - 1) // world * world
             per = n_eval // world
             if args.mg_scheme == "rowblock":
@@ -803,8 +867,9 @@ def main():
               "ms": float(ev_ms), "score_flops_per_s": 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
               "kernel": "tf32_split_kernel x2 + eval_topk_tc_kernel (3xTF32 tcgen05.mma, TMEM accumulators, TMA operands) + "
                         "topk_merge_kernel",
-              "tensor_flops_per_s": 3 * 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
+              "tensor_flops_per_s": 3 * 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3), "scaling": "strong",
               "sharding": "single GPU" if world == 1 else f"user range x{world} (comm-free); item-range variant in eval_item_sharded"}
+        ev["roofline"] = eval_roofline(3 * 2.0 * d * ni * n_eval / world, float(ev_ms))
         if world == 1:
             n_f = min(n_eval, 32768)
             users_f = users[:n_f].contiguous()
@@ -834,23 +899,41 @@ def main():
             extra["configs"] = {"error": str(exc)[:300]}
 
     # ---- same workload on ONE GPU, measured by rank 0 in the same run (for honest strong-scaling ratios) ----
-    if world > 1 and rank == 0:
+    parity = None
+    if world > 1:
+        # every rank recomputes the whole result on its own GPU with the single-GPU path and checks ITS shard of the
+        # multi-GPU result against it (rank 0 also times it: the honest strong-scaling denominator)
         try:
             g1 = ops.Graph(nu, ni, w["rowptr"], w["col"], w["val"])
             out1 = torch.empty((n, d), dtype=torch.float32, device=dev)
-            t1 = timed_steps(lambda: ops.propagate_fwd(g1, w["uw"], w["iw"], L, out=out1), max(2, args.steps // 4), 1, flush, torch)
-            extra["n1_same_workload"] = {"value": nnz * L / (sum(t1) / len(t1) * 1e-3), "ms_per_step": sum(t1) / len(t1)}
-            del g1, out1
+            ops.propagate_fwd(g1, w["uw"], w["iw"], L, out=out1)
+            if args.mg_scheme == "grid":
+                shard = [(out_u[:f1 - f0], out1[f0:f1]), (out_i, out1[nu:])]
+            elif args.mg_scheme == "rowblock":
+                shard = [(out_local, out1[s:e])]
+            else:
+                shard = [(out_u, out1[u0:u1]), (out_i, out1[nu:])]
+            err = torch.tensor([max(norm_rel_err(a, b, torch) for a, b in shard if a.numel())], dtype=torch.float64, device=dev)
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            parity = {"mg_vs_n1_rel_err": float(err), "tolerance": PARITY_TOL, "checked": "every rank's shard of users_emb / items_emb "
+                      "against the single-GPU tgcn_propagate_fwd result recomputed on the same GPU", "ok": bool(float(err) <= PARITY_TOL)}
+            if rank == 0:
+                t1 = timed_steps(lambda: ops.propagate_fwd(g1, w["uw"], w["iw"], L, out=out1), max(2, args.steps // 4), 1, flush, torch)
+                extra["n1_same_workload"] = {"value": nnz * L / (sum(t1) / len(t1) * 1e-3), "ms_per_step": sum(t1) / len(t1)}
+            del g1, out1, shard
         except Exception as exc:  # e.g. out of memory on a shared device
-            extra["n1_same_workload"] = {"error": str(exc)[:200]}
-    if world > 1:
+            parity = {"error": str(exc)[:200], "ok": False}
         dist.barrier()
 
     if world == 1 and not args.no_torch_ref:
         try:
-            extra["torch_cuda_reference"] = torch_cuda_reference(w, dev, flush, torch, args.topk, n_eval=2048 if name == "c5" else 8192)
+            extra["torch_cuda_reference"], ref_emb, ref_ids, ref_sc = torch_cuda_reference(w, dev, flush, torch, args.topk,
+                                                                                           n_eval=2048 if name == "c5" else 8192)
+            parity = parity_vs_torch(ops, graph, out, nu, args.topk, ref_emb, ref_ids, ref_sc, torch)
+            del ref_emb, ref_ids, ref_sc
         except Exception as exc:
             extra["torch_cuda_reference"] = {"error": str(exc)[:300]}
+            parity = {"error": str(exc)[:200], "ok": False}
         torch.cuda.empty_cache()
 
     cpu_base = None
@@ -871,7 +954,7 @@ def main():
         achieved = per_rank_bytes / (ms_per_step * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
+        if world == 1 and os.path.exists(tpath):  # the ncu capture is of the single-GPU launch; N > 1 launches differ
             with open(tpath) as f:
                 traffic = json.load(f).get(name)
         line = {
@@ -892,11 +975,19 @@ def main():
             "eval": ev, "clocks": sampler.summary(),
         }
         line.update(extra)
+        if parity is not None:
+            line["parity"] = parity
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    bad = [p for p in (parity, (extra.get("c2") or {}).get("parity")) if p is not None and not p.get("ok", False)]
+    if extra.get("item_sharded_matches_user_sharded") is False:
+        bad.append({"item_sharded_matches_user_sharded": False})
+    if bad:   # the line above is still printed, but a result out of tolerance fails the run
+        print(f"bench.py: PARITY FAILURE {bad}", file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -9,9 +9,14 @@
  *
  * Conventions
  *   - Every pointer named d_* is a DEVICE pointer, h_* a HOST pointer.  No torch types appear here.
- *   - All matrices are row-major fp32; index arrays are int32; all calls are asynchronous on
- *     `stream` (a cudaStream_t passed as void*), never synchronise, and allocate nothing:
- *     the caller owns inputs, outputs and workspaces.  Only graph handles own device memory.
+ *   - All matrices are row-major fp32; index arrays are int32; every COMPUTE call is asynchronous on
+ *     `stream` (a cudaStream_t passed as void*), never synchronises, and allocates nothing:
+ *     the caller owns inputs, outputs and workspaces.  Only graph handles own device memory, and only
+ *     handle creation (tgcn_graph_create*, tgcn_graph_build_transpose_perm: init-time, like the
+ *     reference's dataset construction) synchronises `stream` and walks the row pointer on the host.
+ *   - A graph handle serialises its own launches: calls that share a handle must be issued on ONE stream
+ *     at a time (the long-row partial sums and arrival counters live in the handle / its workspace);
+ *     a launch on another stream while the previous one is still pending is refused with an error.
  *   - Node numbering follows the reference: rows [0, n_users) are users, rows [n_users, n_users +
  *     n_items) are items (dataset.py:130-131).  N = n_users + n_items.
  *   - Return value 0 = ok; otherwise tgcn_last_error() (thread-local) describes the failure.
@@ -61,10 +66,6 @@ int64_t tgcn_graph_num_segments(const tgcn_graph_t* g);
 /* Eval masks read the user rows of a handle: local row = user id - row_begin, an entry equals col_offset + item id.
  * col_offset defaults to n_users (global column numbering); a row block whose columns are item ids sets 0. */
 int tgcn_graph_set_mask_col_offset(tgcn_graph_t* g, int64_t col_offset);
-/* L2 cache-policy hints for tables larger than L2: rows [0, hot_rows) of the handle gather from the small skewed
- * table (the item table) whose lines are kept with evict_last; everything else streams with evict_first.  Defaults:
- * whole graph = n_users, row block = 0.  hot_rows = -1 disables the hints. */
-int tgcn_graph_set_hot_rows(tgcn_graph_t* g, int64_t hot_rows);
 /* bytes of caller-provided workspace for propagate_fwd / propagate_bwd */
 int64_t tgcn_propagate_workspace_bytes(const tgcn_graph_t* g, int64_t d, int32_t n_layers);
 
@@ -155,6 +156,9 @@ int tgcn_propagate_host(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int3
  * reg_lambda/(2·batch)·(‖U0[users]‖² + ‖I0[pos]‖² + ‖I0[negs]‖²_F) (:200-210).
  * Outputs: d_losses[0] = bpr, d_losses[1] = reg; dL/d(emb) is atomically ADDED into d_grad_emb (N, d)
  * and the regulariser's gradient into d_grad_w0 (N, d) (either may be NULL to skip; caller zeroes).
+ * A row whose user / positive id lies outside [0, n_users) / [0, n_items) — the -1 sentinels tgcn_sample_bpr_batch writes
+ * for rows it could not complete — is skipped (no loss term, no gradient, no memory access); so is a single negative with
+ * such an id.  The divisors stay batch and batch·n_neg.
  * d_workspace holds per-warp partial sums: tgcn_bpr_workspace_bytes(batch). */
 int64_t tgcn_bpr_workspace_bytes(int64_t batch);
 int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch, int32_t n_neg,
@@ -198,6 +202,36 @@ int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_
 int tgcn_adv_select(const tgcn_graph_t* mask_graph, int64_t d, int64_t batch, int32_t n_cand,
                     const int32_t* d_users, const int32_t* d_cands, const float* d_emb, int32_t kmax,
                     int32_t* d_out_negs, int32_t* d_out_counts, float* d_out_scores, tgcn_stream_t stream);
+
+/* a11 / a15 / a18 / a19 / a20 as CALLABLES with the reference's signatures, for callers that want the dense result
+ * rather than the fused top-k (predict / get_loss never come through here: tgcn_eval_topk / tgcn_adv_select fuse these
+ * products so that the intermediates never reach HBM).  Exact fp32 FMA arithmetic.
+ * score_batchwise:  out[m·ldo_row + n·ldo_col] = <A[m, :K], B[n, :K]> (+ d_row_bias[m]) (+ d_col_bias[n]) — BaseModel.
+ *   score_batchwise (base_model.py:173-179: A = users_emb batch, B = items_emb, ldo = (n_items, 1)); one plane of
+ *   LTRBase.get_features_batchwise (ltr_models.py:131-146: ldo = (5·n_items, 5)); LTRLinear(WPop).score_batchwise_ltr
+ *   (ltr_models.py:200-204, :227-232) on the packed operands of tgcn_ltr_pack_* with the head's bias terms.
+ * score_pairwise_adv: out[b, c] = <users_emb[b], items_emb[b, c]> for (batch, d) x (batch, n_cand, d)
+ *   (AdvSamplModel.score_pairwise_adv, advanced_sampling.py:37-44; shape stays (batch, n_cand), no squeeze: G14).
+ * ltr_features_rows: the five dot products of ROW-ALIGNED vectors, reference order [emb·emb, rev·rev, desc·desc, rev·desc,
+ *   desc·rev] (LTRBase.get_features_pairwise(u_vecs, i_vecs), ltr_models.py:148-166) into d_out[b·ldo + 0..4]. */
+int tgcn_score_batchwise(int64_t n_rows, int64_t n_cols, int64_t K, const float* d_a, int64_t lda, const float* d_b,
+                         int64_t ldb, const float* d_row_bias, const float* d_col_bias, float* d_out, int64_t ldo_row,
+                         int64_t ldo_col, tgcn_stream_t stream);
+int tgcn_score_pairwise_adv(int64_t batch, int32_t n_cand, int64_t d, const float* d_users_emb, int64_t ldu,
+                            const float* d_items_emb, float* d_out, tgcn_stream_t stream);
+int tgcn_ltr_features_rows(int64_t batch, int64_t d, int64_t D, const float* d_ue, int64_t ld_ue, const float* d_ie,
+                           int64_t ld_ie, const float* d_ur, int64_t ld_ur, const float* d_ud, int64_t ld_ud,
+                           const float* d_ir, int64_t ld_ir, const float* d_id, int64_t ld_id, float* d_out, int64_t ldo,
+                           tgcn_stream_t stream);
+
+/* a13 / n4  utils.calculate_metrics (utils.py:11-63) on the device: d_pred_ids is the (n_rows, kmax) id table of
+ * tgcn_eval_topk, the true test items of row r are d_true_ids[d_true_ptr[r] .. d_true_ptr[r+1]) (true_test_lil as a CSR).
+ * Writes d_out[ki·5 + m], m = {recall, precision, hit, ndcg, f1} at k = h_ks[ki], each the float64 mean over rows.
+ * Deterministic (fixed-order reduction).  d_workspace: tgcn_topk_metrics_workspace_bytes(). */
+int64_t tgcn_topk_metrics_workspace_bytes(void);
+int tgcn_topk_metrics(int64_t n_rows, int32_t kmax, const int32_t* d_pred_ids, const int64_t* d_true_ptr,
+                      const int32_t* d_true_ids, int32_t n_ks, const int32_t* h_ks, double* d_out, void* d_workspace,
+                      int64_t workspace_bytes, tgcn_stream_t stream);
 
 /* a17-a21  LTR feature assembly (ltr_models.py:116-166, :200-241).
  * pairwise_features: for pair b = (users[b], items[b]) writes the 5 raw dot products

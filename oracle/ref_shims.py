@@ -16,7 +16,21 @@ import types
 import numpy as np
 import scipy.sparse as sp
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def reference_root():
+    """The unmodified reference tree: /root/reference in the authoring container, else the copy that
+    ``__graft_entry__.build()`` leaves in the git-ignored ``baseline/_ref/`` (it travels to the GPU box)."""
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "TextGCN")):
+            return cand
+    return None
+
+
+REFERENCE_ROOT = reference_root() or "/root/reference"
 
 
 class _HeteroGraph:
@@ -50,5 +64,8 @@ def install():
         sys.modules["sentence_transformers"] = st
     if not hasattr(np, "NINF"):
         np.NINF = -np.inf
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "TextGCN")):
+        raise RuntimeError("the reference is neither mounted at /root/reference nor copied to baseline/_ref "
+                           "(run `python -c 'import __graft_entry__ as g; g.build()'` where it is mounted)")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

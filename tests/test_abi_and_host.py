@@ -76,16 +76,12 @@ def test_host_norm_adj_builder_is_bit_exact(case):
     assert np.array_equal(nm.indices()[0].numpy(), g["norm_row"])
 
 
-def test_host_metrics_match_reference_golden():
+def test_truth_csr_host_logic_and_metrics_refuse_cpu():
+    from textgcn_b200 import TgcnError
     from textgcn_b200 import metrics as M
-    for case in ["dummy_lgcn", "small_lgcn_d64", "small_lgcn_d128_l4"]:
-        g = load_golden(case)
-        test = O.train_lists_from_edges(g["test_u"], g["test_i"], int(g["n_users"]))
-        res = M.calculate_metrics(torch.from_numpy(g["pred_ids"]), [test[u].tolist() for u in g["test_users"]], g["ks"].tolist())
-        for m in M.METRICS:
-            assert np.allclose(res[m], g["metric_" + m], rtol=0, atol=1e-12), (case, m)
-    # duplicates in y_true count in the recall denominator, repeated predictions count once (np.intersect1d)
-    res = M.calculate_metrics(torch.tensor([[1, 1, 2]]), [[1, 1, 5]], [3])
-    ref = O.calculate_metrics([[1, 1, 2]], [[1, 1, 5]], [3])
-    for m in M.METRICS:
-        assert np.allclose(res[m], ref[m]), m
+    t = M.TruthCSR.from_lists([[3], [], [2, 2, 7]], "cpu")
+    assert t.ptr.tolist() == [0, 1, 1, 4] and t.ids.tolist() == [3, 2, 2, 7] and t.n_rows == 3
+    p = M.TruthCSR.from_pairs(torch.tensor([2, 0, 2, 2]), torch.tensor([2, 3, 2, 7]), 3)   # order inside a row is kept
+    assert p.ptr.tolist() == t.ptr.tolist() and p.ids.tolist() == t.ids.tolist()
+    with pytest.raises(TgcnError):   # the metric pass is a kernel: no CPU path
+        M.calculate_metrics(torch.tensor([[1, 2, 3]]), [[1]], [3])

@@ -27,7 +27,6 @@ SIGNATURES = {
     "tgcn_graph_destroy": (None, [_P]),
     "tgcn_graph_num_segments": (c_int64, [_P]),
     "tgcn_graph_set_mask_col_offset": (c_int32, [_P, c_int64]),
-    "tgcn_graph_set_hot_rows": (c_int32, [_P, c_int64]),
     "tgcn_propagate_workspace_bytes": (c_int64, [_P, c_int64, c_int32]),
     "tgcn_spmm_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, _P]),
     "tgcn_spmm_ex": (c_int32, [_P, c_int64, _P, _P, _P, c_float, c_int32, c_int32, POINTER(c_void_p), POINTER(c_void_p),
@@ -59,6 +58,12 @@ SIGNATURES = {
     "tgcn_ltr_pairwise_emb_bwd": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "tgcn_ltr_pack_items": (c_int32, [c_int64, c_int64, c_int64, _P, _P, _P, POINTER(c_float), _P, _P]),
     "tgcn_ltr_pack_users": (c_int32, [c_int64, _P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "tgcn_score_batchwise": (c_int32, [c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int64, _P]),
+    "tgcn_score_pairwise_adv": (c_int32, [c_int64, c_int32, c_int64, _P, c_int64, _P, _P, _P]),
+    "tgcn_ltr_features_rows": (c_int32, [c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64,
+                                         _P, c_int64, _P, c_int64, _P]),
+    "tgcn_topk_metrics_workspace_bytes": (c_int64, []),
+    "tgcn_topk_metrics": (c_int32, [c_int64, c_int32, _P, _P, _P, c_int32, POINTER(c_int32), _P, _P, c_int64, _P]),
     "tgcn_sample_bpr_batch": (c_int32, [_P, c_int64, c_int32, _P, ctypes.c_uint64, c_int32, _P, _P, _P]),
     "tgcn_sample_candidates": (c_int32, [c_int64, c_int64, c_int32, _P, ctypes.c_uint64, _P, _P]),
     "tgcn_dropout_mask": (c_int32, [c_int64, c_float, ctypes.c_uint64, _P, _P]),

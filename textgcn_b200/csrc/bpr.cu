@@ -14,7 +14,7 @@ constexpr float kSeluScale = 1.0507009873554804934193349852946f;
 constexpr float kSeluNegCoef = (float)(1.6732632423543772848170429916717 * 1.0507009873554804934193349852946);
 
 struct BprArgs {
-  int n_users, d, batch, n_neg;
+  int n_users, n_items, d, batch, n_neg;
   const int* users;
   const int* pos;
   const int* negs;  // (n_neg, batch)
@@ -41,6 +41,12 @@ __global__ void __launch_bounds__(256) bpr_kernel(const BprArgs a) {
   const int d4 = a.d >> 2;
   const int u = __ldg(a.users + warp);
   const int p = __ldg(a.pos + warp);
+  // Rows the device sampler could not complete carry -1 (tgcn_sample_bpr_batch: a user with no train item, or no
+  // non-positive item left): such a row — or any id outside the tables — contributes nothing and touches no memory.
+  if ((unsigned)u >= (unsigned)a.n_users || (unsigned)p >= (unsigned)a.n_items) {
+    if (lane == 0) a.partials[warp] = make_float2(0.f, 0.f);
+    return;
+  }
   const size_t d = a.d;
   const float* eu_p = a.emb + (size_t)u * d;
   const float* ep_p = a.emb + (size_t)(a.n_users + p) * d;
@@ -69,6 +75,7 @@ __global__ void __launch_bounds__(256) bpr_kernel(const BprArgs a) {
   float loss_sum = 0.f;
   for (int j = 0; j < a.n_neg; ++j) {
     const int n = __ldg(a.negs + (size_t)j * a.batch + warp);
+    if ((unsigned)n >= (unsigned)a.n_items) continue;  // sentinel negative: skipped (warp-uniform)
     const float* en_p = a.emb + (size_t)(a.n_users + n) * d;
     float4 en[kMaxChunks];
     float neg_part = 0.f;
@@ -198,6 +205,7 @@ int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch,
   TGCN_REQUIRE(batch < (1ll << 26), "batch too large");
   BprArgs a;
   a.n_users = (int)n_users;
+  a.n_items = (int)n_items;
   a.d = (int)d;
   a.batch = (int)batch;
   a.n_neg = n_neg;

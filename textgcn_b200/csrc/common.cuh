@@ -63,11 +63,12 @@ struct tgcn_graph {
   int n_segments;
   tgcn::SplitRow* split_rows;
   int n_split_rows;
-  int* split_counters;  // arrivals per split row (self-resetting; one launch in flight per handle)
+  int* split_counters;  // arrivals per split row (self-resetting: ONE launch in flight per handle, enforced by launch_spmm)
+  cudaEvent_t busy_event;    // recorded after every launch that uses the counters / partial-sum scratch ...
+  cudaStream_t busy_stream;  // ... on this stream: a launch on ANOTHER stream while it is pending is refused
+  int busy_valid;
   int max_degree;
   int mask_col_off;  // eval masks: entry value = mask_col_off + item id (n_users unless overridden)
-  int l2_hints;   // allow L2 cache-policy hints on large tables
-  int hot_rows;   // rows [0, hot_rows) gather from the small, skewed table (item table): keep those lines in L2
   int* order;      // owned: rows with <= kSplitThreshold non-zeros, user rows then item rows, each by decreasing
   int n_ordered;   //        number of kUnroll-wide steps (stable), so the lane groups sharing a warp finish together
   int bipartite;  // verified at creation: user rows reference only item columns and vice versa

@@ -581,10 +581,11 @@ static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream) 
   // (LTR, K = 1600: 875 k -> 1003 k users/s).
   *bn = 128;
   if (*stream || (fixed < budget && (budget - fixed) / ((size_t)256 * 128) >= 3)) *bn = 256;
-  {
-    const char* e = getenv("TGCN_EVAL_BN");  // A/B switch
-    if (e && atoi(e) == 128) *bn = 128;
-  }
+  static const bool force_bn128 = [] {  // A/B switch, read once per process
+    const char* e = getenv("TGCN_EVAL_BN");
+    return e && atoi(e) == 128;
+  }();
+  if (force_bn128) *bn = 128;
   const size_t stage = *stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)*bn * 128 : (size_t)*bn * 128;
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;

@@ -1,5 +1,6 @@
 // Graph handle: borrowed CSR of Â + owned load-balancing metadata and transpose permutation.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -120,7 +121,8 @@ static int build_segments(tgcn_graph* g, cudaStream_t stream) {
       if (deg <= kSplitThreshold) order[count[key_of(r, deg)]++] = (int)r;
     }
     g->n_ordered = (int)order.size();
-    if (!order.empty()) {
+    const char* sw = getenv("TGCN_ROW_ORDER");  // A/B switch, read ONCE per handle: 0 = walk the rows in natural order
+    if (!order.empty() && !(sw && atoi(sw) == 0)) {
       TGCN_CHECK_CUDA(cudaMalloc(&g->order, sizeof(int) * order.size()));
       TGCN_CHECK_CUDA(cudaMemcpyAsync(g->order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, stream));
       TGCN_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -181,8 +183,9 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->n_segments = g->n_split_rows = 0;
   g->bipartite = 0;
   g->mask_col_off = (int)n_users;
-  g->l2_hints = 1;
-  g->hot_rows = is_block ? 0 : (int)n_users;
+  g->busy_event = nullptr;
+  g->busy_stream = nullptr;
+  g->busy_valid = 0;
   int rc = build_segments(g, (cudaStream_t)stream);
   if (rc == 0 && nnz > 0) rc = check_rows(g, (cudaStream_t)stream);
   if (rc != 0) {
@@ -240,18 +243,11 @@ void tgcn_graph_destroy(tgcn_graph_t* g) {
   if (g->segments) cudaFree(g->segments);
   if (g->split_rows) cudaFree(g->split_rows);
   if (g->split_counters) cudaFree(g->split_counters);
+  if (g->busy_event) cudaEventDestroy(g->busy_event);
   delete g;
 }
 
 int64_t tgcn_graph_num_segments(const tgcn_graph_t* g) { return g ? g->n_segments : -1; }
-
-int tgcn_graph_set_hot_rows(tgcn_graph_t* g, int64_t hot_rows) {
-  TGCN_REQUIRE(g != nullptr, "graph is NULL");
-  TGCN_REQUIRE(hot_rows >= -1 && hot_rows <= g->n_rows, "hot_rows out of range");
-  g->l2_hints = hot_rows >= 0;
-  g->hot_rows = hot_rows < 0 ? 0 : (int)hot_rows;
-  return 0;
-}
 
 int tgcn_graph_set_mask_col_offset(tgcn_graph_t* g, int64_t col_offset) {
   TGCN_REQUIRE(g != nullptr, "graph is NULL");

@@ -1,13 +1,14 @@
-// K-layer LightGCN propagation: CSR SpMM with warp-per-row gathers, 128-bit loads, edge-dropout
-// applied as a keep-mask over the static CSR, and the layer-mean fused into the last pass.
+// K-layer LightGCN propagation: CSR SpMM with 128-bit gathers, edge dropout applied as a keep-mask over
+// the static CSR, and the layer mean fused into the last pass.
 //
 // Roofline: HBM-bound.  Algorithmic bytes per layer = nnz·(4d + 8) + N·4d + (N+1)·4.
 //
-// Work decomposition: one warp per row; the warp's lanes are split into G = 32/LPN groups of LPN
-// lanes, each lane owning VPL float4 of the d-wide row (d = 4·LPN·VPL), so G non-zeros are gathered
-// per step and kBatch non-zeros are in flight per warp.  Rows longer than kSplitThreshold are cut
-// into kSegmentLen-nnz segments handled by separate warps that write partial sums; the last segment
-// of a row to finish adds the partials in fixed order, so results are deterministic run to run.
+// Work decomposition (spmm_group_kernel, every width the models use): one GROUP of LPN lanes per row, each lane
+// owning VPL float4 of the d-wide output row (d = 4·LPN·VPL) and walking the row's non-zeros itself — no shuffles, no
+// cross-lane reduction; several rows share a warp when LPN < 32.  Rows longer than kSplitThreshold are cut into
+// kSegmentLen-nnz segments handled by separate groups that write partial sums; the last segment of a row to finish
+// adds the partials in slot order, so results are deterministic run to run.  spmm_rows_kernel (warp per row, lanes
+// split over non-zeros) serves the odd widths.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -48,8 +49,6 @@ struct SpmmArgs {
   const float* x_user;  // gather source: c < x_split ? x_user + c·d : x_item + (c - x_split)·d
   const float* x_item;
   int x_split;
-  int hot_rows;  // rows [0, hot_rows) gather from a table worth keeping in L2 (evict_last); -1 = no cache hints
-  int hint_mode;  // bit 0: evict_last on hot gathers, bit 1: evict_first on cold gathers, bit 2: evict_first on col/val
   int n_rows;
   int n_units;       // row units of the group / slice kernels: n_rows, or the number of short rows when `order` is set
   const int* order;  // short rows (<= kSplitThreshold non-zeros) by decreasing step count, or NULL
@@ -224,44 +223,6 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
   }
 }
 
-// L2 cache-policy hints — EXPERIMENTAL, off unless TGCN_L2_MODE is set (bit 0: evict_last on the item-table gathers
-// of user rows, bit 1: evict_first on the user-table gathers, bit 2: evict_first on the col/val stream).  Idea: at the
-// 200M-edge config the tables exceed the 126 MB L2 (ncu: 11 % L2 hit rate, 184 GB DRAM traffic per layer at 82 % of
-// DRAM peak) and the item table is small and popularity-skewed.  Measured on B200: every mode was 3-8 % slower than
-// plain ld.global.nc (116.3 ms/step without, 120.5-125.8 ms with), so the default stays hint-free.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ldg4_hint(const float* ptr, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int ldg_hint_i32(const int* ptr, uint64_t pol) {
-  int v;
-  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float ldg_hint_f32(const float* ptr, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
-  return v;
-}
-
 // ---- main kernel (exact widths d = 4·LPN·VPL) -----------------------------------------------------------
 // One GROUP of LPN lanes per row (two rows per warp at d = 64, four at d = 32, one at d >= 128): each lane owns
 // VPL float4 columns of the output row and walks the row's non-zeros itself, kUnroll at a time, so there are
@@ -271,9 +232,12 @@ __device__ __forceinline__ float ldg_hint_f32(const float* ptr, uint64_t pol) {
 // integer/address work, and 39 % achieved occupancy from 256-thread blocks waiting on their longest row; this
 // layout issues ~5 per non-zero and uses 128-thread blocks.
 constexpr int kUnroll = 4;
+#ifndef TGCN_DEFAULT_LANES_D64
+#define TGCN_DEFAULT_LANES_D64 16
+#endif
 constexpr int kGroupThreads = 128;
 
-template <int LPN, int VPL, bool HINT>
+template <int LPN, int VPL>
 __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArgs a) {
   constexpr int D = 4 * LPN * VPL;
   const int tid = blockIdx.x * kGroupThreads + threadIdx.x;
@@ -304,25 +268,13 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
 #pragma unroll
   for (int w = 0; w < VPL; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool masked = a.keep != nullptr;
-  uint64_t pol_stream = 0, pol_x = 0;
-  if (HINT) {
-    const uint64_t normal = l2_policy_evict_normal();
-    pol_stream = (a.hint_mode & 4) ? l2_policy_evict_first() : normal;
-    pol_x = row < a.hot_rows ? ((a.hint_mode & 1) ? l2_policy_evict_last() : normal)
-                             : ((a.hint_mode & 2) ? l2_policy_evict_first() : normal);
-  }
   // col/val of step p (c < 0: no gather — past the row end or a dropped edge)
   auto load_cv = [&](int p, int (&c)[kUnroll], float (&v)[kUnroll]) {
 #pragma unroll
     for (int i = 0; i < kUnroll; ++i) {
       const bool ok = p + i < end;
-      if (HINT) {
-        c[i] = ok ? ldg_hint_i32(a.col + p + i, pol_stream) : -1;
-        v[i] = ok ? ldg_hint_f32(a.val + p + i, pol_stream) : 0.f;
-      } else {
-        c[i] = ok ? __ldg(a.col + p + i) : -1;
-        v[i] = ok ? __ldg(a.val + p + i) : 0.f;
-      }
+      c[i] = ok ? __ldg(a.col + p + i) : -1;
+      v[i] = ok ? __ldg(a.val + p + i) : 0.f;
     }
     if (masked) {
 #pragma unroll
@@ -346,9 +298,7 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     for (int i = 0; i < kUnroll; ++i)
 #pragma unroll
       for (int w = 0; w < VPL; ++w)
-        x[i][w] = c[i] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
-                  : HINT   ? ldg4_hint(xb + (size_t)c[i] * D + w * (LPN * 4), pol_x)
-                           : ldg4(xb + (size_t)c[i] * D + w * (LPN * 4));
+        x[i][w] = c[i] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(xb + (size_t)c[i] * D + w * (LPN * 4));
 #pragma unroll
     for (int i = 0; i < kUnroll; ++i)
 #pragma unroll
@@ -429,8 +379,50 @@ template <int LPN, int VPL>
 static void launch_group(const SpmmArgs& a, cudaStream_t s) {
   const int64_t units = (int64_t)a.n_segments + (LPN < 32 ? a.n_units : a.n_rows);
   const int64_t blocks = (units * LPN + kGroupThreads - 1) / kGroupThreads;
-  if (a.hot_rows >= 0) spmm_group_kernel<LPN, VPL, true><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
-  else spmm_group_kernel<LPN, VPL, false><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
+  spmm_group_kernel<LPN, VPL><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
+}
+
+// Lane layout per width, read ONCE per process (A/B switches for profiling; the defaults are the measured best):
+// TGCN_SPMM_LANES_D64 / _D128 = lanes per row (16 | 8 at d = 64, 32 | 16 at d = 128); fewer lanes = more rows per warp, two
+// float4 per lane, half the (group-redundant) col / val / address instructions per non-zero.
+struct SpmmTuning {
+  int lanes_d64, lanes_d128;
+};
+static const SpmmTuning& spmm_tuning() {
+  static const SpmmTuning t = [] {
+    SpmmTuning v{TGCN_DEFAULT_LANES_D64, 32};
+    if (const char* e = getenv("TGCN_SPMM_LANES_D64")) v.lanes_d64 = atoi(e) == 8 ? 8 : 16;
+    if (const char* e = getenv("TGCN_SPMM_LANES_D128")) v.lanes_d128 = atoi(e) == 16 ? 16 : 32;
+    return v;
+  }();
+  return t;
+}
+
+// The long-row scratch (partial sums in the caller's workspace, arrival counters in the handle) is per HANDLE, so two
+// launches on one handle may only overlap if they are ordered on one stream.  Same-stream launches are; a launch on a
+// different stream while the previous one has not finished is refused.  (Skipped during stream capture: a captured
+// graph replays with the dependencies it was captured with.)
+static int handle_guard_enter(const tgcn_graph* g, cudaStream_t s, bool* record) {
+  *record = false;
+  if (g->n_segments == 0) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (g->busy_valid && g->busy_stream != s)
+    TGCN_REQUIRE(cudaEventQuery(g->busy_event) != cudaErrorNotReady,
+                 "graph handle is busy on another stream: launches sharing a handle must be ordered on one stream");
+  *record = true;
+  return 0;
+}
+static void handle_guard_exit(const tgcn_graph* cg, cudaStream_t s) {
+  tgcn_graph* g = const_cast<tgcn_graph*>(cg);
+  if (!g->busy_event && cudaEventCreateWithFlags(&g->busy_event, cudaEventDisableTiming) != cudaSuccess) return;
+  if (cudaEventRecord(g->busy_event, s) == cudaSuccess) {
+    g->busy_stream = s;
+    g->busy_valid = 1;
+  }
 }
 
 static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
@@ -438,12 +430,17 @@ static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
   const int threads = 256;
   const int64_t blocks = (warps * 32 + threads - 1) / threads;
   TGCN_REQUIRE(blocks < (1ll << 31), "grid too large");
+  bool record = false;
+  if (int rc = handle_guard_enter(g, s, &record)) return rc;
   const int d = a.d;
   const bool contiguous = a.x_split == 0x7fffffff || a.x_item == a.x_user + (size_t)a.x_split * d;
   const bool group_ok = g->bipartite || contiguous;  // per-row table select needs a bipartite Â or one table
+  const SpmmTuning& tune = spmm_tuning();
   if (group_ok && d == 16) launch_group<4, 1>(a, s);
   else if (group_ok && d == 32) launch_group<8, 1>(a, s);
+  else if (group_ok && d == 64 && tune.lanes_d64 == 8) launch_group<8, 2>(a, s);
   else if (group_ok && d == 64) launch_group<16, 1>(a, s);
+  else if (group_ok && d == 128 && tune.lanes_d128 == 16) launch_group<16, 2>(a, s);
   else if (group_ok && d == 128) launch_group<32, 1>(a, s);
   else if (group_ok && d == 256) launch_group<32, 2>(a, s);
   else if (d <= 16) spmm_rows_kernel<4, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
@@ -454,6 +451,7 @@ static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
   else if (d <= 512) spmm_rows_kernel<32, 4><<<(unsigned)blocks, threads, 0, s>>>(a);
   else TGCN_REQUIRE(false, "embedding width %d > 512 is not supported", d);
   TGCN_CHECK_LAUNCH();
+  if (record) handle_guard_exit(g, s);
   return 0;
 }
 
@@ -475,12 +473,8 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.keep_div = 1.f;
   a.keep_scale = 1.f;
   a.n_rows = (int)g->n_rows;
-  {
-    const char* m = getenv("TGCN_ROW_ORDER");  // A/B switch: 0 = rows in natural order
-    const bool use = g->order != nullptr && !(m && atoi(m) == 0);
-    a.order = use ? g->order : nullptr;
-    a.n_units = use ? g->n_ordered : (int)g->n_rows;
-  }
+  a.order = g->order;  // NULL when the handle was created with the row order switched off (TGCN_ROW_ORDER=0 at creation)
+  a.n_units = g->order ? g->n_ordered : (int)g->n_rows;
   a.d = (int)d;
   a.segments = g->segments;
   a.n_segments = g->n_segments;
@@ -492,12 +486,6 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.ep.accumulate = 0;
   a.ep.n_peers = 0;
   a.x_split = g->is_block ? 0x7fffffff : (int)g->n_users;
-  // cache hints only pay when the gathered tables exceed L2 (~126 MB); hot_rows < 0 disables them
-  {
-    const char* m = getenv("TGCN_L2_MODE");
-    a.hint_mode = m ? atoi(m) : 0;  // off by default: measured 3-8 % SLOWER at the 200M-edge config (profiles/r01/README.md)
-  }
-  a.hot_rows = (g->l2_hints && a.hint_mode != 0 && (int64_t)(g->n_users + g->n_items) * d * 4 > (96ll << 20)) ? g->hot_rows : -1;
 }
 
 struct ScatterSpec {  // destination of the last pass in feature-sliced mode (see Epilogue)

@@ -1,13 +1,17 @@
 """Multi-GPU hot path on one NVSwitch box: one process per GPU, torch.distributed (NCCL) for the plumbing.
 
-Propagation: Â is partitioned by ROW BLOCK, balanced by nnz.  Rank p owns rows [starts[p], starts[p+1]) and the
-matching rows of every layer's embedding table.  One hop = all-gather of the P row blocks (padded to a common
-``max_rows`` so the collective is a single contiguous ``all_gather_into_tensor``) followed by the local SpMM,
-whose column indices were relabelled once, at partition time, to index the padded gathered table directly.  The
-layer mean is local (fused into the last SpMM's epilogue).
+Propagation, default scheme (``GridPropagator``, ``bench.py --gpus N``): a G x R grid of feature slices x user
+partitions.  E' = Â·E acts on every embedding column independently, so the FEATURE dimension splits with no exchange per
+hop; inside a slice the users are partitioned by nnz, the (6x smaller) item-table slice is all-reduced once per hop
+within the row group of R ranks, overlapped with the user-row SpMM, and the change of layout at the end rides in the
+last passes as peer-memory stores (CUDA IPC over NVLink).  ``BipartitePropagator`` is the G = 1 hop loop it builds on,
+``SlicedPropagator`` the G = P case as one C-ABI call per rank.
 
-A second scheme (``BipartitePropagator``, the default of ``bench.py --gpus N``) exploits the bipartite structure: users are
-partitioned, the 6x smaller item table is replicated and all-reduced once per hop, overlapping the user-row SpMM.
+The north_star's wording — Â partitioned by ROW BLOCK with an all-gather of layer embeddings between hops — is
+``DistPropagator``: rank p owns rows [starts[p], starts[p+1]) (balanced by nnz); one hop = all-gather of the P row blocks
+(padded to a common ``max_rows`` so the collective is a single contiguous ``all_gather_into_tensor``) + the local SpMM,
+whose column indices were relabelled once to index the padded gathered table.  It is comm-bound (5.1 GB per hop per
+rank at the 200M-edge config) and kept as the comparison arm.
 
 Evaluation: sharded by ITEM range (north_star).  Every rank ranks all requested users against its item shard
 with the fused score+mask+top-k kernel, the (U, k) partial tables are exchanged with an all-to-all so that rank p
@@ -184,6 +188,7 @@ class BipartitePropagator:
         self.ubufs = [torch.empty((self.n_local, d), dtype=torch.float32, device=device) for _ in range(max(n_layers - 1, 0))]
         self.ibufs = [torch.empty((part.n_items, d), dtype=torch.float32, device=device) for _ in range(n_layers)]
         self.comm_bytes_per_hop = part.n_items * d * 4  # all-reduce payload per rank
+        self._probe = os.environ.get("TGCN_MG_PROBE", "")  # "nocomm" / "nocompute": timing probes for the overlap analysis, read once
 
     def propagate(self, e0_user_local: torch.Tensor, e0_item: torch.Tensor, out_user_local: torch.Tensor,
                   out_item: torch.Tensor, single: bool = False):
@@ -191,7 +196,7 @@ class BipartitePropagator:
         Writes this rank's rows of users_emb and the whole items_emb."""
         L = self.n_layers
         ws = self.part.world_size
-        probe = os.environ.get("TGCN_MG_PROBE", "")  # "nocomm" / "nocompute": timing probes for the overlap analysis only
+        probe = self._probe
         spmm = (lambda *a: None) if probe == "nocompute" else self.spmm_fn
 
         def item_partials(src_u, dst):

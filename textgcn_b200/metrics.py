@@ -1,63 +1,61 @@
-"""recall / precision / hit / ndcg / f1 @k computed from the (n, k) id table (reference: utils.py:11-63).
+"""recall / precision / hit / ndcg / f1 @k from the (n, k) id table on the device (reference: utils.py:11-63).
 
-Vectorised restatement that runs on the device holding the predictions: the reference's
-pandas row-apply takes 65 % of ``evaluate``.  Semantics kept: the intersection counts distinct predicted ids
-found in y_true (np.intersect1d, utils.py:46), recall divides by len(y_true) with duplicates (:15-16, :39),
-ndcg uses log2(arange(2, k+2)) discounts and an ideal of min(|y_true|, k) ones (:23-33), f1 is 0 where
-precision + recall is 0 (:55-62); every metric is the mean over rows.
+SURVEY.md §8f n4: the reference's pandas row-apply takes 65 % of ``evaluate`` and ingests a Python list per user.  Here
+the true test items are a CSR (``TruthCSR``: ptr int64 (n+1), ids int32) resident on the device and ONE kernel
+(``tgcn_topk_metrics``, csrc/metrics.cu) turns the (n, kmax) id table of the fused eval kernel into the five metrics
+for every k — no Python loop over users, 10M users in a few milliseconds.  Semantics are the reference's (distinct
+intersection, recall over len(y_true) with duplicates, ndcg relevance on every occurrence, f1 = 0 where the
+denominator is 0, float64 means).  There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List, Sequence, Union
 
 import numpy as np
 import torch
 
+from . import ops
+from ._lib import TgcnError
+
 METRICS = ["recall", "precision", "hit", "ndcg", "f1"]
 
 
-def pad_lists(lists: Sequence[Sequence[int]], device) -> torch.Tensor:
-    width = max(1, max((len(x) for x in lists), default=1))
-    out = np.full((len(lists), width), -1, dtype=np.int64)
-    for r, x in enumerate(lists):
-        out[r, :len(x)] = np.asarray(x, dtype=np.int64)
-    return torch.from_numpy(out).to(device)
+class TruthCSR:
+    """``true_test_lil`` (base_model.py:57, dataset.py:118-120) as a device CSR: row r lists the test items of the r-th
+    ranked user."""
+
+    def __init__(self, ptr: torch.Tensor, ids: torch.Tensor):
+        self.ptr, self.ids = ptr, ids
+
+    @property
+    def n_rows(self) -> int:
+        return self.ptr.numel() - 1
+
+    @classmethod
+    def from_lists(cls, lists: Sequence[Sequence[int]], device) -> "TruthCSR":
+        """From the reference's list of lists (one flat concatenation on the host, done once per model)."""
+        lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+        ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        flat = np.fromiter((i for x in lists for i in x), dtype=np.int32, count=int(ptr[-1]))
+        return cls(torch.from_numpy(ptr).to(device), torch.from_numpy(flat).to(device))
+
+    @classmethod
+    def from_pairs(cls, rows: torch.Tensor, items: torch.Tensor, n_rows: int) -> "TruthCSR":
+        """From (row, item) pairs already on the device (any order; the order inside a row is kept): torch ops only."""
+        rows = rows.to(torch.int64)
+        order = torch.argsort(rows, stable=True)
+        ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=rows.device)
+        ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n_rows), 0)
+        return cls(ptr, items[order].to(torch.int32).contiguous())
 
 
-def calculate_metrics(pred_ids: torch.Tensor, y_true: Sequence[Sequence[int]], ks: Sequence[int]) -> Dict[str, List[float]]:
-    dev = pred_ids.device
-    pred = pred_ids.to(torch.int64)
-    true = pad_lists(y_true, dev)
-    true_len = torch.tensor([len(x) for x in y_true], dtype=torch.float64, device=dev)
-    res = {m: [] for m in METRICS}
-    n = pred.shape[0]
-    kmax = pred.shape[1]
-    hits = torch.zeros((n, kmax), dtype=torch.bool, device=dev)
-    step = max(1, (1 << 24) // max(1, kmax * true.shape[1]))
-    for s in range(0, n, step):
-        p = pred[s:s + step]
-        hits[s:s + step] = ((p[:, :, None] == true[s:s + step][:, None, :]) & (p[:, :, None] >= 0)).any(-1)
-    # a predicted id repeated inside the list counts once (np.intersect1d returns unique values)
-    first = torch.ones_like(hits)
-    if kmax > 1:
-        same = pred[:, :, None] == pred[:, None, :]
-        earlier = torch.tril(torch.ones(kmax, kmax, dtype=torch.bool, device=dev), diagonal=-1)
-        first = ~(same & earlier[None]).any(-1)
-    for k in sorted(ks):
-        h = hits[:, :k]
-        inter = (h & first[:, :k]).sum(1).to(torch.float64)
-        rec = inter / true_len
-        prec = inter / k
-        disc = 1.0 / torch.log2(torch.arange(2, k + 2, dtype=torch.float64, device=dev))
-        ideal_n = torch.clamp(true_len, max=k).to(torch.int64)
-        idcg = torch.cumsum(disc, 0)[ideal_n - 1]
-        # rel = isin(y_pred[:k], intersection): every occurrence of a hit id counts in the dcg (utils.py:31)
-        ndcg = (h.to(torch.float64) * disc).sum(1) / idcg
-        den = rec + prec
-        f1 = torch.where(den != 0, rec * prec * 2 / torch.where(den != 0, den, torch.ones_like(den)), torch.zeros_like(den))
-        res["recall"].append(float(rec.mean()))
-        res["precision"].append(float(prec.mean()))
-        res["hit"].append(float((inter > 0).to(torch.float64).mean()))
-        res["ndcg"].append(float(ndcg.mean()))
-        res["f1"].append(float(f1.mean()))
-    return res
+def calculate_metrics(pred_ids: torch.Tensor, y_true: Union[TruthCSR, Sequence[Sequence[int]]], ks: Sequence[int]
+                      ) -> Dict[str, List[float]]:
+    """{metric: [value at each k of sorted(ks)]} like utils.calculate_metrics (utils.py:36-63)."""
+    if not isinstance(pred_ids, torch.Tensor) or not pred_ids.is_cuda:
+        raise TgcnError("calculate_metrics needs the CUDA id table of predict_device (textgcn_b200 has no CPU path)")
+    truth = y_true if isinstance(y_true, TruthCSR) else TruthCSR.from_lists(y_true, pred_ids.device)
+    ks = sorted(int(k) for k in ks)
+    vals = ops.topk_metrics(pred_ids.to(torch.int32).contiguous(), truth.ptr, truth.ids, ks).cpu().numpy()
+    return {m: [float(vals[ki, mi]) for ki in range(len(ks))] for mi, m in enumerate(METRICS)}

@@ -1,11 +1,11 @@
 """Host-side mirror of the reference's model API over the sm_100a kernels.
 
 The reference's plugin surface is Python method override on ``BaseModel``.  ``B200HotPath``
-overrides exactly the hot-path methods — ``representation``, ``layer_aggregation``, ``get_loss`` / ``bpr_loss``,
-``predict``, ``evaluate`` — keeping names, argument meaning and return types, so it can be mixed in front of the
-reference's own classes or used with the standalone classes below, which restate the thin
-non-hot-path shell (constructor contract, ``fit`` loop, checkpointing) so the package runs where the reference
-is not installed.  State-dict keys are the reference's (``embedding_user.weight``, ``embedding_item.weight``,
+overrides exactly the hot-path methods — ``representation``, ``layer_aggregation``, ``score_batchwise``, ``get_loss`` /
+``bpr_loss``, ``predict``, ``evaluate`` — keeping names, argument meaning and return types, so it can be mixed in front
+of the reference's own classes (``textgcn_b200.dropin``; exercised on the GPU over the unmodified
+reference by tests/test_gpu_dropin.py) or used with the standalone classes below, which supply a small shell of their
+own (constructor contract, training loop, checkpoint files) so the package also runs where the reference is absent.  State-dict keys are the reference's (``embedding_user.weight``, ``embedding_item.weight``,
 ``layers.N.weight/bias``), so checkpoints interchange.
 
 All compute goes through ``textgcn_b200.ops`` -> libtgcn_b200.so.  There is no CPU path: constructing a model on
@@ -15,14 +15,12 @@ from __future__ import annotations
 
 import os
 import random
-import shutil
 from collections import defaultdict
 from types import SimpleNamespace
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
-from torch import nn
 
 from . import metrics as M
 from . import ops
@@ -125,6 +123,37 @@ class _LtrPairFeaturesFn(torch.autograd.Function):
         return grad_emb, None, None, None, None, None
 
 
+class _ScoreBatchwiseFn(torch.autograd.Function):
+    """score_batchwise (base_model.py:173-179) as a kernel call.  The reference only ever calls it under no_grad
+    (predict); should a caller differentiate through it anyway, the two transposed products are left to torch."""
+
+    @staticmethod
+    def forward(ctx, users_emb, items_emb):
+        ctx.save_for_backward(users_emb, items_emb)
+        return ops.score_batchwise(users_emb.detach(), items_emb.detach())
+
+    @staticmethod
+    def backward(ctx, grad):
+        u, i = ctx.saved_tensors
+        return (grad @ i if ctx.needs_input_grad[0] else None), (grad.t() @ u if ctx.needs_input_grad[1] else None)
+
+
+class _PairFeatRowsFn(torch.autograd.Function):
+    """get_features_pairwise(u_vecs, i_vecs) (ltr_models.py:148-166): (B, 5) from one kernel; only feature 0 carries a
+    gradient (the text vectors are constants), d f0 / d ue = ie, d f0 / d ie = ue ((B, d) elementwise glue)."""
+
+    @staticmethod
+    def forward(ctx, ue, ie, ur, ud, ir, idesc):
+        ctx.save_for_backward(ue, ie)
+        return ops.ltr_features_rows(ue.detach(), ie.detach(), ur, ud, ir, idesc)
+
+    @staticmethod
+    def backward(ctx, grad_f):
+        ue, ie = ctx.saved_tensors
+        g0 = grad_f[:, :1]
+        return (g0 * ie if ctx.needs_input_grad[0] else None), (g0 * ue if ctx.needs_input_grad[1] else None), None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # the hot-path overrides
 # ------------------------------------------------------------------------------------------------
@@ -133,6 +162,7 @@ class B200HotPath:
 
     dropout_rng = "host"  # "host": torch.rand on the CPU generator like base_model.py:82; "device": CUDA generator
     eval_precision = "auto"  # "fp32" = exact FMA kernel; "3xtf32" = tcgen05 tensor cores; "auto" = 3xTF32 when eligible
+    strict_fused = False  # True: the methods that would materialise dense intermediates raise instead (score_batchwise, ...)
 
     # -- graph ---------------------------------------------------------------------------------
     @property
@@ -185,7 +215,18 @@ class B200HotPath:
         return torch.sum(users_emb * items_emb, dim=1)
 
     def score_batchwise(self, users_emb, items_emb, users):
-        raise TgcnError("score_batchwise is fused into predict(): the dense (B, n_items) score matrix is never materialised")
+        """base_model.py:173-179: (B, d) x (n_items, d) -> (B, n_items) fp32, for callers that want the matrix (exact-fp32
+        SGEMM kernel, csrc/dense.cu).  ``predict`` does NOT come through here: it never materialises the matrix."""
+        if self.strict_fused:
+            raise TgcnError("strict_fused: score_batchwise would materialise the dense (B, n_items) score matrix; use predict()")
+        return _ScoreBatchwiseFn.apply(users_emb, items_emb)
+
+    def _add_loss(self, name, value):
+        """``_loss_values[name] += value`` (base_model.py:197, :209); the reference only creates the dict inside fit()."""
+        lv = self.__dict__.get("_loss_values")
+        if lv is None:
+            lv = self._loss_values = defaultdict(float)
+        lv[name] += value
 
     def _split_batch(self, data):
         dev = self.graph.device
@@ -202,8 +243,8 @@ class B200HotPath:
         """base_model.py:181-184: (B, 2 + n_neg) int64 batch -> bpr + reg, both from one fused kernel."""
         users, pos, negs = self._split_batch(data)
         losses = self._fused_losses(users, pos, negs, self.reg_lambda)
-        self._loss_values["bpr"] += losses[0].detach()
-        self._loss_values["reg"] += losses[1].detach()
+        self._add_loss("bpr", losses[0].detach())
+        self._add_loss("reg", losses[1].detach())
         return losses[0] + losses[1]
 
     def bpr_loss(self, users, pos, negs):
@@ -211,16 +252,16 @@ class B200HotPath:
         dev = self.graph.device
         negs_t = torch.stack([torch.as_tensor(n) for n in negs]) if not isinstance(negs, torch.Tensor) else negs
         losses = self._fused_losses(ops.as_index(users, dev), ops.as_index(pos, dev), ops.as_index(negs_t, dev), 0.0)
-        self._loss_values["bpr"] += losses[0].detach()
+        self._add_loss("bpr", losses[0].detach())
         return losses[0]
 
     def reg_loss(self, users, pos, negs):
-        """base_model.py:200-210 on layer-0 rows (B·(2 + n_neg)·d floats: left to torch)."""
-        negs_t = torch.stack(list(negs)) if not isinstance(negs, torch.Tensor) else negs
-        loss = (self.embedding_user(users).norm(2).pow(2) + self.embedding_item(pos).norm(2).pow(2)
-                + self.embedding_item(negs_t).norm(2).pow(2).mean())
-        res = self.reg_lambda * loss / len(users) / 2
-        self._loss_values["reg"] += res.detach()
+        """base_model.py:200-210, when called on its own (get_loss takes it from the fused kernel): the squared norms of
+        B·(2 + n_neg) layer-0 rows — O(B·d) glue left to torch."""
+        negs_t = negs if isinstance(negs, torch.Tensor) else torch.stack(list(negs))
+        sq = sum(w(ix).square().sum() for w, ix in ((self.embedding_user, users), (self.embedding_item, pos), (self.embedding_item, negs_t)))
+        res = sq * (self.reg_lambda / (2 * len(users)))
+        self._add_loss("reg", res.detach())
         return res
 
     # -- a11..a13 ------------------------------------------------------------------------------
@@ -264,165 +305,15 @@ class B200HotPath:
         self.eval()
         self.training = False
         ids, _ = self.predict_device(self.test_users)
-        results = M.calculate_metrics(ids, self.true_test_lil, self.k)
+        truth = self.__dict__.get("_b200_truth")
+        if truth is None or truth[0] is not self.true_test_lil:   # true_test_lil as a device CSR, built once per model
+            truth = self.__dict__["_b200_truth"] = (self.true_test_lil, M.TruthCSR.from_lists(self.true_test_lil, ids.device))
+        results = M.calculate_metrics(ids, truth[1], self.k)
         self.logger.info(" " * 11 + "".join([f"@{i:<6}" for i in self.k]))
         for i in results:
             self.metrics_logger[i] = np.append(self.metrics_logger[i], [results[i]], axis=0)
             self.logger.info(f"{i:11}" + " ".join([f"{j:.4f}" for j in results[i]]))
         return results
-
-
-# ------------------------------------------------------------------------------------------------
-# standalone shell (constructor contract, fit loop, checkpointing: base_model.py:23-75, :108-139, :278-299)
-# ------------------------------------------------------------------------------------------------
-def early_stop(res) -> bool:
-    """utils.py:79-90."""
-    if len(res["recall"]) < 3:
-        return False
-    declining = all(np.less(m[-1], m[-2]).all() and np.less(m[-2], m[-3]).all() for m in res.values())
-    converged = all(np.allclose(m[-1], m[-2], atol=1e-4) for m in res.values()) and \
-        all(np.allclose(m[-1], m[-3], atol=1e-4) for m in res.values())
-    return converged or declining
-
-
-class BaseModel(B200HotPath, nn.Module):
-    """LightGCN with BPR; same constructor contract as the reference: ``Model(params, dataset)``."""
-
-    def __init__(self, params, dataset):
-        super().__init__()
-        self._copy_params(params)
-        self._copy_dataset_params(dataset)
-        self._init_embeddings(params.emb_size)
-        self._add_vars(params)
-        self.load_model(getattr(params, "load", None))
-        self.to(params.device)
-
-    def _copy_params(self, params):
-        for name in ["k", "lr", "uid", "save", "quiet", "epochs", "logger", "device", "dropout", "emb_size", "n_layers",
-                     "save_path", "batch_size", "reg_lambda", "evaluate_every", "neg_samples"]:
-            setattr(self, name, getattr(params, name))
-        self.device = torch.device(self.device)
-        if self.device.type != "cuda":
-            raise TgcnError("textgcn_b200 models need a CUDA device: there is no CPU fallback")
-        self.slurm = params.slurm or params.quiet
-        if getattr(params, "single", False):
-            self.layer_combination = self.layer_combination_single
-        self.fused_adam = getattr(params, "fused_adam", False)
-        self.dropout_rng = getattr(params, "dropout_rng", "host")
-        self.eval_precision = getattr(params, "eval_precision", "auto")
-        self.nan_check = getattr(params, "nan_check", "step")
-        self.cuda_graph = getattr(params, "cuda_graph", False)  # replay the training step from one CUDA graph (train_graph.py)
-
-    def _copy_dataset_params(self, dataset):
-        self.n_users = dataset.n_users
-        self.n_items = dataset.n_items
-        self.norm_matrix = dataset.norm_matrix
-        self.true_test_lil = dataset.true_test_lil
-        self.train_user_dict = getattr(dataset, "train_user_dict", None)
-        if hasattr(dataset, "test_users"):
-            self.test_users = np.asarray(dataset.test_users)
-        else:
-            self.test_users = np.sort(dataset.test_df.user_id.unique())
-        if hasattr(dataset, "user_mapping"):
-            self.user_mapping_dict = dict(dataset.user_mapping[["remap_id", "org_id"]].values)
-            self.item_mapping_dict = dict(dataset.item_mapping[["remap_id", "org_id"]].values)
-        if getattr(dataset, "graph", None) is not None:
-            self.__dict__["_b200_graph"] = dataset.graph
-
-    def _init_embeddings(self, emb_size):
-        self.embedding_user = nn.Embedding(num_embeddings=self.n_users, embedding_dim=emb_size).to(self.device)
-        self.embedding_item = nn.Embedding(num_embeddings=self.n_items, embedding_dim=emb_size).to(self.device)
-        nn.init.normal_(self.embedding_user.weight, std=0.1)
-        nn.init.normal_(self.embedding_item.weight, std=0.1)
-
-    def _add_vars(self, params):
-        self.metrics = list(M.METRICS)
-        self.metrics_logger = {i: np.zeros((0, len(self.k))) for i in self.metrics}
-        self.training = False
-        self._loss_values = defaultdict(float)
-
-    def layer_combination(self, vectors):
-        """base_model.py:150-157 (kept for API parity; `representation` fuses it into the last SpMM pass)."""
-        return torch.mean(torch.stack(vectors), axis=0)
-
-    def layer_combination_single(self, vectors):
-        return vectors[-1]
-
-    @property
-    def embedding_matrix(self):
-        return torch.cat([self.embedding_user.weight, self.embedding_item.weight])
-
-    def fit(self, batches):
-        """base_model.py:108-139."""
-        graphed = None
-        if self.cuda_graph and type(self).get_loss is B200HotPath.get_loss:  # fixed-shape BPR steps only (not AdvSampl / LTR)
-            from .optim import FusedAdam
-            from .train_graph import GraphedTrainStep
-            self.optimizer = FusedAdam(self.parameters(), lr=self.lr, capturable=True)
-            graphed = GraphedTrainStep(self, self.optimizer)
-        elif self.fused_adam:
-            from .optim import FusedAdam
-            self.optimizer = FusedAdam(self.parameters(), lr=self.lr)
-        else:
-            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.lr)
-        for epoch in range(1, self.epochs + 1):
-            self.train()
-            self.training = True
-            self._loss_values = defaultdict(float)
-            epoch_loss = 0
-            nan_seen = torch.zeros((), dtype=torch.bool, device=self.device)
-            for data in batches:
-                if graphed is not None:
-                    batch_loss = graphed(data)
-                    nan_seen |= batch_loss.isnan()
-                    epoch_loss += batch_loss
-                    continue
-                self.optimizer.zero_grad()
-                batch_loss = self.get_loss(data)
-                if self.nan_check == "step":  # the reference's per-step device sync (base_model.py:123, SURVEY.md G7)
-                    assert not batch_loss.isnan(), f"loss is NA at epoch {epoch}"
-                else:                          # same check without draining the stream every step
-                    nan_seen |= batch_loss.detach().isnan()
-                epoch_loss += batch_loss.detach()
-                batch_loss.backward()
-                self.optimizer.step()
-            assert not bool(nan_seen), f"loss is NA at epoch {epoch}"
-            if graphed is not None:  # the graph accumulates [bpr, reg] in place; hand the epoch's sums to the logger
-                sums = graphed.loss_sums.clone()
-                graphed.loss_sums.zero_()
-                self._loss_values["bpr"], self._loss_values["reg"] = sums[0], sums[1]
-            if epoch % self.evaluate_every:
-                continue
-            self.logger.info(f"Epoch {epoch}: {' '.join([f'{k} = {float(v):.4f}' for k, v in self._loss_values.items()])}")
-            self.evaluate(epoch)
-            self.checkpoint(epoch)
-            if early_stop(self.metrics_logger):
-                self.logger.warning(f"Early stopping triggerred at epoch {epoch}")
-                break
-        else:
-            self.checkpoint(self.epochs)
-
-    def load_model(self, load_path):
-        """base_model.py:278-289."""
-        if load_path is None:
-            return
-        if os.path.isdir(load_path):
-            load_path = os.path.join(load_path, "best.pkl")
-        self.logger.info(f"Loading model {load_path}")
-        self.load_state_dict(torch.load(load_path, map_location=self.device))
-        self.logger.info("Performance of the loaded model:")
-        self.evaluate()
-        self.metrics_logger = {i: np.zeros((0, len(self.k))) for i in self.metrics}
-
-    def checkpoint(self, epoch):
-        """base_model.py:291-299."""
-        if not self.save:
-            return
-        os.makedirs(self.save_path, exist_ok=True)
-        torch.save(self.state_dict(), os.path.join(self.save_path, "latest_checkpoint.pkl"))
-        if self.metrics_logger[self.metrics[0]][:, 0].max() == self.metrics_logger[self.metrics[0]][-1][0]:
-            self.logger.info(f"Updating best model at epoch {epoch}")
-            shutil.copyfile(os.path.join(self.save_path, "latest_checkpoint.pkl"), os.path.join(self.save_path, "best.pkl"))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -434,7 +325,12 @@ class B200AdvSampl:
     positive_sampler = "host"  # "host": Python random.sample like the reference; "device": keyed permutation kernel
 
     def score_pairwise_adv(self, users_emb, items_emb):
-        raise TgcnError("score_pairwise_adv is fused into get_loss(): the (B, 1000, d) gather is never materialised")
+        """advanced_sampling.py:37-44: (B, d) x (B, C, d) -> (B, C), for callers that hold the gathered candidates
+        (csrc/dense.cu).  ``get_loss`` does NOT come through here: ``tgcn_adv_select`` scores the candidates straight from
+        the embedding table, so the (B, 1000, d) gather is never materialised.  Shape stays (B, C) for B == 1 (G14)."""
+        if self.strict_fused:
+            raise TgcnError("strict_fused: score_pairwise_adv needs the materialised (B, C, d) gather; use get_loss()")
+        return ops.score_pairwise_adv(users_emb.detach(), items_emb.detach())
 
     def _sample_positives_device(self, users: torch.Tensor) -> torch.Tensor:
         """Device counterpart of ``_sample_positives`` (advanced_sampling.py:63-64), (B, pos_samples) int64, -1 padded."""
@@ -448,7 +344,8 @@ class B200AdvSampl:
         return out
 
     def _sample_positives(self, users: Sequence[int]) -> torch.Tensor:
-        """advanced_sampling.py:63-64: <= pos_samples random positives per user from Python's RNG, -1 padded."""
+        """advanced_sampling.py:63-64: <= pos_samples random positives per user from Python's RNG (one ``random.sample``
+        per batch row, in row order: a seeded run consumes the generator exactly like the reference), -1 padded."""
         out = np.full((len(users), self.pos_samples), -1, dtype=np.int64)
         for b, u in enumerate(users):
             positives = self.positive_lists[u]["list"]
@@ -481,24 +378,29 @@ class B200AdvSampl:
         return super().get_loss(self.select_triples(data))
 
 
-class AdvSamplModel(B200AdvSampl, BaseModel):
-    def _copy_params(self, params):
-        super()._copy_params(params)
-        self.positive_sampler = getattr(params, "positive_sampler", "host")
-
-    def _copy_dataset_params(self, dataset):
-        super()._copy_dataset_params(dataset)
-        self.positive_lists = getattr(dataset, "positive_lists", None)
-        self.pos_samples = getattr(dataset, "pos_samples", 5)
-
-
 # ------------------------------------------------------------------------------------------------
 # (e) learning to rank on top of LightGCN  (ltr_models.py:38-241)
 # ------------------------------------------------------------------------------------------------
-class B200LTR:
-    """Overrides of LTRBase / LTRLinear / LTRLinearWPop."""
+def _covers_all(index, n: int) -> bool:
+    return isinstance(index, range) and index == range(n)
 
-    with_pop = False
+
+class B200LTR:
+    """Overrides of LTRBase / LTRLinear / LTRLinearWPop.
+
+    LTRLinear re-binds ``evaluate`` / ``score_pairwise`` / ``score_batchwise`` to their ``*_ltr`` versions by instance
+    attribute at the END of its constructor (ltr_models.py:172-179), so that a base model loaded inside ``_add_vars``
+    (``--load_base``) is evaluated with plain LightGCN scoring first (G18).  This mixin supplies the ``*_ltr`` methods, so
+    that re-binding lands on the kernel-backed versions, and uses the same marker — "has the instance been re-bound
+    yet?" — to decide how ``predict`` ranks."""
+
+    with_pop = None  # None: LTRLinearWPop is recognised by its popularity tables (ltr_models.py:216-219)
+
+    def _has_pop(self) -> bool:
+        return bool(self.with_pop) if self.with_pop is not None else hasattr(self, "popularity_users")
+
+    def _ltr_active(self) -> bool:
+        return "score_batchwise" in self.__dict__ and "layers" in self._modules
 
     def _tabs(self):
         t = self.__dict__.get("_b200_tabs")
@@ -511,7 +413,7 @@ class B200LTR:
         return t
 
     def _pop(self):
-        if not self.with_pop:
+        if not self._has_pop():
             return None
         p = self.__dict__.get("_b200_pop")
         if p is None:
@@ -531,21 +433,87 @@ class B200LTR:
             w = layer.weight.detach().double() @ w
         return w.reshape(-1), b.reshape(())
 
+    # -- a17: the vectors behind the features (ltr_models.py:116-128) ------------------------------
+    def _rows(self, table: torch.Tensor, index) -> torch.Tensor:
+        if _covers_all(index, table.shape[0]):
+            return table  # `self.all_items`: the table itself, no (n_items, D) copy
+        return table[torch.as_tensor(np.asarray(index) if not isinstance(index, torch.Tensor) else index, device=table.device).long()]
+
+    def get_user_vectors(self, users_emb, users):
+        t = self._tabs()
+        return {"emb": users_emb, "desc": self._rows(t["users_desc"], users), "reviews": self._rows(t["users_rev"], users)}
+
+    def get_item_vectors(self, items_emb, items):
+        t = self._tabs()
+        return {"emb": items_emb, "desc": self._rows(t["items_desc"], items), "reviews": self._rows(t["items_rev"], items)}
+
+    # -- a18 / a19: features with the reference's signatures ----------------------------------------
+    def get_features_batchwise(self, u_vecs, i_vecs):
+        """ltr_models.py:131-146: (B, n_items, 5) — five SGEMM kernel calls writing the planes in place (no cat).
+        ``predict`` does NOT come through here (``_rank`` folds the head into one contraction and never builds the planes)."""
+        if self.strict_fused:
+            raise TgcnError("strict_fused: get_features_batchwise would materialise five dense (B, n_items) planes; use predict()")
+        pairs = (("emb", "emb"), ("reviews", "reviews"), ("desc", "desc"), ("reviews", "desc"), ("desc", "reviews"))
+        B, n = u_vecs["emb"].shape[0], i_vecs["emb"].shape[0]
+        out = torch.empty((B, n, len(pairs)), dtype=torch.float32, device=u_vecs["emb"].device)
+        for f, (ku, ki) in enumerate(pairs):
+            ops.score_batchwise(u_vecs[ku].detach(), i_vecs[ki].detach(), out=out, plane=f)
+        return out
+
+    def get_features_pairwise(self, u_vecs, i_vecs):
+        """ltr_models.py:148-166: (B, 5) from one kernel over the row-aligned vectors; differentiable w.r.t. the 'emb' pair."""
+        return _PairFeatRowsFn.apply(u_vecs["emb"], i_vecs["emb"], u_vecs["reviews"], u_vecs["desc"], i_vecs["reviews"], i_vecs["desc"])
+
     def get_features_pairwise_fused(self, emb, users, items):
-        """ltr_models.py:148-166 (+ popularity columns :234-241) from one gather kernel."""
+        """The same features (+ popularity columns, ltr_models.py:234-241) gathered by id inside one kernel — what
+        ``bpr_loss`` uses, so that the six (B, ·) gathers are never materialised."""
         dev = self.graph.device
         return _LtrPairFeaturesFn.apply(emb, self.n_users, ops.as_index(users, dev), ops.as_index(items, dev), self._tabs(), self._pop())
 
-    def score_pairwise_ltr(self, users_emb, items_emb, users, items):
-        """ltr_models.py:206-210 / :234-241 -> (B, 1).  ``users_emb``/``items_emb`` are the gathered rows."""
-        tabs, pop = self._tabs(), self._pop()
-        def sm(x, y):
-            return (x * y).sum(dim=1).unsqueeze(1)
-        ur, ud, ir, idesc = tabs["users_rev"][users], tabs["users_desc"][users], tabs["items_rev"][items], tabs["items_desc"][items]
-        f = torch.cat([sm(users_emb, items_emb), sm(ur, ir), sm(ud, idesc), sm(ur, idesc), sm(ud, ir)], dim=1)
+    # -- a20 / a21: scores -------------------------------------------------------------------------
+    def _packed_items(self, items_emb, w):
+        t = self._tabs()
+        return ops.ltr_pack_items(items_emb.detach().contiguous(), t["items_rev"], t["items_desc"], w[:5].tolist())
+
+    def _head_bias(self, users, w, b, device):
+        """(user_bias (B,), item_bias (n_items,) | None): the head's bias and the popularity columns of the collapsed head."""
+        pop = self._pop()
+        user_bias = torch.full((users.numel(),), float(b), dtype=torch.float32, device=device)
+        item_bias = None
         if pop is not None:
-            f = torch.cat([f, pop[0][users], pop[1][items]], dim=-1)
+            user_bias = (user_bias.double() + w[5] * pop[0][users.long(), 0].double()).float().contiguous()
+            item_bias = (w[6] * pop[1][:, 0].double()).float().contiguous()
+        return user_bias, item_bias
+
+    def score_batchwise_ltr(self, users_emb, items_emb, users):
+        """ltr_models.py:200-204 / :227-232 -> (B, n_items): the head is affine (no activations, G16), so the five (seven)
+        feature planes collapse into ONE product of width d + 2D with per-user / per-item bias — one SGEMM kernel call
+        instead of five GEMMs, a cat and a Linear.  (B == 1 keeps its leading dimension: the reference's squeeze, G14/G15.)"""
+        if self.strict_fused:
+            raise TgcnError("strict_fused: score_batchwise_ltr would materialise the dense (B, n_items) matrix; use predict()")
+        t = self._tabs()
+        w, b = self.collapsed_head()
+        dev = items_emb.device
+        users_t = torch.as_tensor(np.asarray(users) if not isinstance(users, torch.Tensor) else users, device=dev).long()
+        users_p = torch.cat([users_emb.detach(), t["users_rev"][users_t], t["users_desc"][users_t]], dim=1)
+        user_bias, item_bias = self._head_bias(users_t, w, b, dev)
+        return ops.score_batchwise(users_p, self._packed_items(items_emb, w), row_bias=user_bias, col_bias=item_bias)
+
+    def score_pairwise_ltr(self, users_emb, items_emb, users, items):
+        """ltr_models.py:206-210 / :234-241 -> (B, 1) (G15).  ``users_emb`` / ``items_emb`` are the gathered rows."""
+        f = self.get_features_pairwise(self.get_user_vectors(users_emb, users), self.get_item_vectors(items_emb, items))
+        pop = self._pop()
+        if pop is not None:
+            f = torch.cat([f, pop[0][users.long()], pop[1][items.long()]], dim=-1)
         return self.layers(f)
+
+    def evaluate_ltr(self, *args, **kwargs):
+        """ltr_models.py:192-198: log the head's feature weights, then the fused evaluate."""
+        if len(self.layers) == 1:
+            self.logger.info("Feature weights from the top layer:")
+            for f, w in zip(self.feature_names, self.layers[0].weight.tolist()[0]):
+                self.logger.info(f"{f:<20} {w:.4}")
+        return B200HotPath.evaluate(self, *args, **kwargs)
 
     def bpr_loss(self, users, pos, negs):
         """base_model.py:186-198 with the LTR pairwise score: fused feature gathers + the tiny head in torch."""
@@ -557,7 +525,7 @@ class B200LTR:
             neg_scores = self.layers(self.get_features_pairwise_fused(out, users, neg))
             loss = loss + torch.mean(torch.nn.functional.selu(neg_scores - pos_scores))
         loss = loss / len(negs)
-        self._loss_values["bpr"] += loss.detach()
+        self._add_loss("bpr", loss.detach())
         return loss
 
     def get_loss(self, data):
@@ -565,80 +533,19 @@ class B200LTR:
         return self.bpr_loss(users, pos, negs) + self.reg_loss(users, pos, negs)
 
     def _rank(self, emb, users, k):
-        """score_batchwise_ltr (ltr_models.py:200-204, :227-232) + mask + top-k as ONE contraction of width
-        d + 2·D: the head is affine, so its weights are folded into the packed item operand."""
-        tabs, pop = self._tabs(), self._pop()
+        """score_batchwise_ltr + mask + top-k as ONE tensor-core contraction of width d + 2·D (the head's weights folded
+        into the packed item operand, its bias terms into one extra K-chunk).  Until the constructor has re-bound the
+        scoring methods (a base model being loaded and evaluated inside ``_add_vars``, G18) the ranking is plain LightGCN's."""
+        if not self._ltr_active():
+            return B200HotPath._rank(self, emb, users, k)
+        tabs = self._tabs()
         w, b = self.collapsed_head()
         nu = self.n_users
-        items_p = ops.ltr_pack_items(emb[nu:], tabs["items_rev"], tabs["items_desc"], w[:5].tolist())
+        items_p = self._packed_items(emb[nu:], w)
         users_p = ops.ltr_pack_users(users, emb[:nu], tabs["users_rev"], tabs["users_desc"])
-        user_bias = torch.full((users.numel(),), float(b), dtype=torch.float32, device=emb.device)
-        item_bias = None
-        if pop is not None:
-            user_bias = (user_bias.double() + w[5] * pop[0][users.long(), 0].double()).float().contiguous()
-            item_bias = (w[6] * pop[1][:, 0].double()).float().contiguous()
+        user_bias, item_bias = self._head_bias(users, w, b, emb.device)
         return ops.eval_topk(self.graph, users_p, items_p, k, users=users, user_bias=user_bias, item_bias=item_bias,
                              by_position=True, precision=self.eval_precision)
 
 
-class LTRLinear(B200LTR, BaseModel):
-    def _copy_params(self, params):
-        super()._copy_params(params)
-        self.load_base = getattr(params, "load_base", None)
-        self.freeze = getattr(params, "freeze", False)
-
-    def _copy_dataset_params(self, dataset):
-        super()._copy_dataset_params(dataset)
-        self.items_as_avg_reviews = dataset.items_as_avg_reviews
-        self.users_as_avg_reviews = dataset.users_as_avg_reviews
-        self.users_as_avg_desc = dataset.users_as_avg_desc
-        self.items_as_desc = dataset.items_as_desc
-        self.all_items = getattr(dataset, "all_items", range(dataset.n_items))
-
-    def _init_embeddings(self, emb_size):
-        super()._init_embeddings(emb_size)
-        if self.freeze:
-            self.embedding_user.requires_grad_(False)
-            self.embedding_item.requires_grad_(False)
-
-    def _add_vars(self, params):
-        super()._add_vars(params)
-        self._ltr_ready = False
-        if self.load_base:  # base model is loaded and evaluated with plain LightGCN scoring first (G18)
-            self.load_model(self.load_base)
-        self.feature_names = ["lightgcn score", "reviews", "desc", "reviews-description", "description-reviews"]
-        self._setup_layers(params)
-        self._ltr_ready = True
-
-    def _setup_layers(self, params):
-        layer_sizes = [len(self.feature_names)] + list(getattr(params, "ltr_layers", [])) + [1]
-        self.layers = nn.Sequential(*[nn.Linear(i, j) for i, j in zip(layer_sizes, layer_sizes[1:])]).to(self.device)
-
-    def _rank(self, emb, users, k):
-        if not self._ltr_ready:
-            return B200HotPath._rank(self, emb, users, k)
-        return B200LTR._rank(self, emb, users, k)
-
-    def get_loss(self, data):
-        return B200LTR.get_loss(self, data)
-
-    def evaluate(self, *args, **kwargs):
-        """ltr_models.py:192-198."""
-        if len(self.layers) == 1:
-            self.logger.info("Feature weights from the top layer:")
-            for f, w in zip(self.feature_names, self.layers[0].weight.tolist()[0]):
-                self.logger.info(f"{f:<20} {w:.4}")
-        return super().evaluate(*args, **kwargs)
-
-
-class LTRLinearWPop(LTRLinear):
-    with_pop = True
-
-    def _copy_dataset_params(self, dataset):
-        super()._copy_dataset_params(dataset)
-        self.popularity_users = dataset.popularity_users
-        self.popularity_items = dataset.popularity_items
-
-    def _setup_layers(self, params):
-        self.feature_names += ["user popularity", "item popularity"]
-        super()._setup_layers(params)
+from .standalone import AdvSamplModel, BaseModel, LTRLinear, LTRLinearWPop, early_stop  # noqa: E402,F401  (re-exported)

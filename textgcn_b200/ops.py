@@ -111,13 +111,18 @@ class Graph:
         nbytes = max(int(self.lib.tgcn_propagate_workspace_bytes(self.handle, d, n_layers)), 256)
         ws = self._ws.get("buf")
         if ws is None or ws.numel() < nbytes:
+            if self._ws.get("pinned"):
+                raise _lib.TgcnError("the workspace of this graph handle is referenced by a captured CUDA graph and cannot grow "
+                                     f"(needs {nbytes} bytes for d={d}, L={n_layers}); use a second Graph handle for the wider call")
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws["buf"] = ws
         return ws
 
-    def set_hot_rows(self, n: int) -> None:
-        """Rows [0, n) gather from the small table to keep in L2 (evict_last hints); -1 disables cache hints."""
-        check(self.lib.tgcn_graph_set_hot_rows(self.handle, int(n)))
+    def pin_workspace(self) -> None:
+        """Called after a CUDA graph has captured launches on this handle: the captured kernels hold the workspace's address,
+        so it must neither move nor be freed; later calls that would need a larger one raise instead of reallocating.
+        (One workspace per handle also means one stream per handle at a time — the library refuses a concurrent launch.)"""
+        self._ws["pinned"] = True
 
     def set_mask_col_offset(self, off: int) -> None:
         check(self.lib.tgcn_graph_set_mask_col_offset(self.handle, int(off)))
@@ -488,6 +493,105 @@ def ltr_pack_users(users: Optional[torch.Tensor], users_emb, users_rev, users_de
         check(lib.tgcn_ltr_pack_users(n, _ptr(users), d, D, _ptr(_chk(users_emb, torch.float32, "users_emb")),
                                       _ptr(_chk(users_rev, torch.float32, "users_rev")),
                                       _ptr(_chk(users_desc, torch.float32, "users_desc")), _ptr(out), _stream()))
+    return out
+
+
+def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    """fp32 CUDA matrix whose rows are contiguous, 16-byte aligned and start every stride(0) % 4 == 0 floats (a column
+    slice of a wider table qualifies: no copy)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.TgcnError(f"{name} must be a CUDA tensor (textgcn_b200 has no CPU path)")
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise _lib.TgcnError(f"{name} must be a 2-D fp32 tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.stride(0) < t.shape[1] or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t
+
+
+def score_batchwise(a: torch.Tensor, b: torch.Tensor, row_bias: Optional[torch.Tensor] = None,
+                    col_bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                    plane: Optional[int] = None) -> torch.Tensor:
+    """out[m, n] = <a[m], b[n]> (+ row_bias[m]) (+ col_bias[n]) in exact fp32 — base_model.py:173-179 as a kernel call.
+    ``out`` (M, N) by default; with ``plane = f`` the result is written to out[:, :, f] of a contiguous (M, N, F) tensor
+    (the feature planes of ltr_models.py:131-146)."""
+    lib = _lib.load()
+    a, b = _rows2d(a, "a"), _rows2d(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K or K % 4 != 0:
+        raise _lib.TgcnError("operands must share a width that is a multiple of 4")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _chk(out, torch.float32, "out", align=4)
+    if plane is None:
+        if out.shape != (M, N):
+            raise _lib.TgcnError("out must be (M, N)")
+        ptr, ldr, ldc = out.data_ptr(), N, 1
+    else:
+        if out.dim() != 3 or out.shape[:2] != (M, N) or not 0 <= plane < out.shape[2]:
+            raise _lib.TgcnError("out must be (M, N, F) with 0 <= plane < F")
+        F = out.shape[2]
+        ptr, ldr, ldc = out.data_ptr() + 4 * plane, N * F, F
+    if M == 0 or N == 0:
+        return out
+    rb = None if row_bias is None else _chk(row_bias, torch.float32, "row_bias", align=4)
+    cb = None if col_bias is None else _chk(col_bias, torch.float32, "col_bias", align=4)
+    with torch.cuda.device(a.device):
+        check(lib.tgcn_score_batchwise(M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(rb), _ptr(cb), ptr, ldr, ldc,
+                                       _stream()))
+    return out
+
+
+def score_pairwise_adv(users_emb: torch.Tensor, items_emb: torch.Tensor) -> torch.Tensor:
+    """(B, d) x (B, C, d) -> (B, C): advanced_sampling.py:37-44 as a kernel call (shape kept for B == 1, G14)."""
+    lib = _lib.load()
+    u = _rows2d(users_emb, "users_emb")
+    it = _chk(items_emb.contiguous(), torch.float32, "items_emb", 3)
+    B, C, d = it.shape
+    if u.shape != (B, d) or d % 4 != 0:
+        raise _lib.TgcnError("users_emb must be (B, d) for items_emb (B, C, d), d % 4 == 0")
+    out = torch.empty((B, C), dtype=torch.float32, device=u.device)
+    if B * C:
+        with torch.cuda.device(u.device):
+            check(lib.tgcn_score_pairwise_adv(B, C, d, u.data_ptr(), u.stride(0), it.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def ltr_features_rows(ue, ie, ur, ud, ir, idesc) -> torch.Tensor:
+    """(B, 5) features of row-aligned vectors (ltr_models.py:148-166)."""
+    lib = _lib.load()
+    ts = [_rows2d(t, n) for t, n in ((ue, "u emb"), (ie, "i emb"), (ur, "u reviews"), (ud, "u desc"), (ir, "i reviews"), (idesc, "i desc"))]
+    B, d = ts[0].shape
+    D = ts[2].shape[1]
+    if ts[1].shape != (B, d) or any(t.shape != (B, D) for t in ts[2:]) or d % 4 or D % 4:
+        raise _lib.TgcnError("feature vectors must be row-aligned: emb (B, d), text (B, D), widths multiples of 4")
+    out = torch.empty((B, 5), dtype=torch.float32, device=ts[0].device)
+    if B:
+        args = []
+        for t in ts:
+            args += [t.data_ptr(), t.stride(0)]
+        with torch.cuda.device(out.device):
+            check(lib.tgcn_ltr_features_rows(B, d, D, *args, out.data_ptr(), 5, _stream()))
+    return out
+
+
+def topk_metrics(pred_ids: torch.Tensor, true_ptr: torch.Tensor, true_ids: torch.Tensor, ks: Sequence[int]) -> torch.Tensor:
+    """(len(ks), 5) float64 means of [recall, precision, hit, ndcg, f1] (utils.py:36-63) from the (n, kmax) int32 id
+    table and the CSR (ptr int64 (n+1), ids int32) of true test items; one kernel + a fixed-order reduction."""
+    lib = _lib.load()
+    pred = _chk(pred_ids, torch.int32, "pred_ids", 2, align=4)
+    tp = _chk(true_ptr, torch.int64, "true_ptr", 1, align=8)
+    ti = _chk(true_ids, torch.int32, "true_ids", 1, align=4)
+    n, kmax = pred.shape
+    if tp.numel() != n + 1:
+        raise _lib.TgcnError("true_ptr must have n_rows + 1 entries")
+    ks = [int(k) for k in ks]
+    out = torch.empty((len(ks), 5), dtype=torch.float64, device=pred.device)
+    ws = torch.empty(int(lib.tgcn_topk_metrics_workspace_bytes()), dtype=torch.uint8, device=pred.device)
+    arr = (ctypes.c_int32 * len(ks))(*ks)
+    with torch.cuda.device(pred.device):
+        check(lib.tgcn_topk_metrics(n, kmax, pred.data_ptr(), tp.data_ptr(), ti.data_ptr(), len(ks), arr, out.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _stream()))
     return out
 
 

@@ -64,6 +64,7 @@ class GraphedTrainStep:
             with torch.cuda.device(self.device), torch.cuda.graph(g):
                 self.static_loss = self._step(self.static_batch)
             self.graph = g
+            self.model.graph.pin_workspace()  # the captured launches hold its address
             g.replay()
             return self.static_loss
         # warm-up steps (real steps: parameter gradients and optimizer state must exist before capture) and odd shapes

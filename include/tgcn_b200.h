@@ -135,6 +135,28 @@ int tgcn_peer_alloc(int64_t bytes, void** d_ptr, uint8_t* h_handle);
 int tgcn_peer_open(const uint8_t* h_handle, void** d_ptr);
 int tgcn_peer_close(void* d_ptr);
 int tgcn_peer_free(void* d_ptr);
+/* Stream-ordered barrier between the n_peers GPUs that share peer-mapped flag arrays (h_peer_flags[q] = rank q's array of
+ * n_peers int64 slots, zero-initialised, opened with tgcn_peer_open): returns on `stream` once every peer has reached the
+ * barrier with the same `epoch` (1, 2, 3, ... — strictly increasing per call).  One tiny kernel; replaces the 1-float NCCL
+ * all-reduce that bracketed the peer stores of the grid / sliced schemes.  Everything this GPU stored to peer memory on
+ * `stream` before the call is visible to the peers after their barrier returns. */
+int tgcn_peer_barrier(int32_t n_peers, int32_t rank, int64_t* const* h_peer_flags, int64_t epoch, tgcn_stream_t stream);
+
+/* e (multi-GPU)  The path's collectives as helpers that take an ncclComm_t (passed as void*; any communicator of the
+ * process, e.g. one created below).  unique_id / init_rank / destroy: communicator plumbing for consumers that do not run
+ * torch.distributed — rank 0 of the group fills the 128-byte id, ships it over any transport, every rank calls init_rank.
+ * allreduce_sum_f32: the per-hop exchange of the grid / bipartite schemes — in-place sum of the (n_items, d/G) item-table
+ *   slice over the row group.  allgather_f32: the north_star's row-block scheme — every rank contributes n_per_rank floats.
+ * topk_exchange: item-sharded eval — block q (rows_per_rank x k) of the partial tables goes to rank q; afterwards
+ *   d_recv_* holds, block by block, every shard's candidates for THIS rank's user slice, ready for tgcn_topk_merge. */
+#define TGCN_COMM_ID_BYTES 128
+int tgcn_comm_unique_id(uint8_t* h_id);
+int tgcn_comm_init_rank(void** comm, int32_t n_ranks, int32_t rank, const uint8_t* h_id);
+int tgcn_comm_destroy(void* comm);
+int tgcn_allreduce_sum_f32(void* comm, float* d_buf, int64_t n, tgcn_stream_t stream);
+int tgcn_allgather_f32(void* comm, const float* d_send, float* d_recv, int64_t n_per_rank, tgcn_stream_t stream);
+int tgcn_topk_exchange(void* comm, int32_t n_ranks, int64_t rows_per_rank, int32_t k, const int32_t* d_part_ids,
+                       const float* d_part_scores, int32_t* d_recv_ids, float* d_recv_scores, tgcn_stream_t stream);
 
 /* Backward of the above (what autograd does at base_model.py:125 through :148/:157): given
  * d_grad_out = dL/d(out) (N, d) computes dL/dE0 into d_grad_in (N, d) with L transposed SpMMs in

@@ -69,9 +69,35 @@ def _worker(rank, world, port, ret):
         merged_identical = bool(torch.equal(a_ids, b_ids) and torch.equal(a_sc, b_sc))
         dist.barrier()
         sp.close()
-        ok = sliced_identical and merged_identical and all(
+        # the same two exchanges through the C-ABI communicator (tgcn_comm_*, tgcn_allreduce_sum_f32, tgcn_topk_exchange):
+        # grid 1 x 2 with the per-hop all-reduce on the library's own ncclComm_t, single-layer output through the p2p
+        # exchange, item-sharded eval with the partial tables exchanged by tgcn_topk_exchange
+        comm = tdist.CabiComm(list(range(world)), rank, dev)
+        gp = tdist.GridPartition(rowptr, nu, ni, d, 1, 2)
+        u0, u1 = gp.rows.users(rank)
+        ug = ops.Graph(nu, ni, *gp.rows.user_block(rank, rowptr, col, val), row_begin=u0, block=True)
+        ig = ops.Graph(nu, ni, *gp.rows.item_block(rank, rowptr, col, val), row_begin=nu, block=True)
+        prop = tdist.GridPropagator(gp, rank, ug, ig, L, dev, exchange="p2p", comm=comm)
+        h0, h1 = gp.final_users(rank)
+        ref_single = ops.propagate_fwd(whole, uw, iw, L, single=True)
+        for single, want in ((False, ref), (True, ref_single), (False, ref)):
+            g_u, g_i = prop.propagate(uw[u0:u1].contiguous(), iw, single=single)
+            torch.cuda.synchronize()
+            errs[("cabi", 2, "single" if single else "mean")] = max(float((g_u - want[h0:h1]).abs().max() / want.abs().max()),
+                                                                   float((g_i - want[nu:]).abs().max() / want.abs().max()))
+        c_ids, c_sc = tdist.sharded_eval_topk(whole, ref[:nu], ref[nu:], users, k, rank, world, gather=True, comm=comm)
+        cabi_identical = bool(torch.equal(a_ids, c_ids) and torch.equal(a_sc, c_sc))
+        send = torch.full((5,), float(rank + 1), device=dev)
+        recv = torch.empty(5 * world, device=dev)
+        ops.comm_allgather(comm.handle, send, recv)
+        torch.cuda.synchronize()
+        gathered_ok = recv.view(world, 5).eq(torch.arange(1, world + 1, device=dev, dtype=torch.float32)[:, None]).all().item()
+        dist.barrier()
+        prop.close()
+        comm.close()
+        ok = sliced_identical and merged_identical and cabi_identical and gathered_ok and all(
             e <= (0.0 if key[1] == 1 else 1e-6) for key, e in errs.items())
-        ret[rank] = "ok" if ok else f"mismatch: {errs} sliced={sliced_identical} merged={merged_identical}"
+        ret[rank] = "ok" if ok else f"mismatch: {errs} sliced={sliced_identical} merged={merged_identical} cabi={cabi_identical}"
     except Exception:  # pragma: no cover
         import traceback
         ret[rank] = traceback.format_exc()

@@ -43,6 +43,13 @@ SIGNATURES = {
     "tgcn_peer_open": (c_int32, [_P, POINTER(c_void_p)]),
     "tgcn_peer_close": (c_int32, [_P]),
     "tgcn_peer_free": (c_int32, [_P]),
+    "tgcn_peer_barrier": (c_int32, [c_int32, c_int32, POINTER(c_void_p), c_int64, _P]),
+    "tgcn_comm_unique_id": (c_int32, [_P]),
+    "tgcn_comm_init_rank": (c_int32, [POINTER(c_void_p), c_int32, c_int32, _P]),
+    "tgcn_comm_destroy": (c_int32, [_P]),
+    "tgcn_allreduce_sum_f32": (c_int32, [_P, _P, c_int64, _P]),
+    "tgcn_allgather_f32": (c_int32, [_P, _P, _P, c_int64, _P]),
+    "tgcn_topk_exchange": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P]),
     "tgcn_propagate_bwd": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, c_float, c_int32, _P, _P, c_int64, _P]),
     "tgcn_propagate_host": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, c_int64, _P]),
     "tgcn_bpr_workspace_bytes": (c_int64, [c_int64]),

@@ -67,6 +67,9 @@ struct tgcn_graph {
   cudaEvent_t busy_event;    // recorded after every launch that uses the counters / partial-sum scratch ...
   cudaStream_t busy_stream;  // ... on this stream: a launch on ANOTHER stream while it is pending is refused
   int busy_valid;
+  int n_user_segments;       // segments [0, n_user_segments) belong to user rows (whole-graph handles; all of them for a block)
+  cudaStream_t host_in, host_out;  // tgcn_propagate_host: copy streams + events, created on first use
+  cudaEvent_t host_ev[13];
   int max_degree;
   int mask_col_off;  // eval masks: entry value = mask_col_off + item id (n_users unless overridden)
   int* order;      // owned: rows with <= kSplitThreshold non-zeros, user rows then item rows, each by decreasing

@@ -130,6 +130,9 @@ static int build_segments(tgcn_graph* g, cudaStream_t stream) {
   }
   g->max_degree = max_deg;
   g->n_segments = (int)segs.size();
+  g->n_user_segments = 0;  // segments are emitted in row order: those of rows < n_users come first
+  for (const Segment& sg : segs)
+    if (g->is_block || sg.row < g->n_users) g->n_user_segments++;
   g->n_split_rows = (int)splits.size();
   if (!segs.empty()) {
     TGCN_CHECK_CUDA(cudaMalloc(&g->segments, sizeof(Segment) * segs.size()));
@@ -186,6 +189,9 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->busy_event = nullptr;
   g->busy_stream = nullptr;
   g->busy_valid = 0;
+  g->n_user_segments = 0;
+  g->host_in = g->host_out = nullptr;
+  for (auto& e : g->host_ev) e = nullptr;
   int rc = build_segments(g, (cudaStream_t)stream);
   if (rc == 0 && nnz > 0) rc = check_rows(g, (cudaStream_t)stream);
   if (rc != 0) {
@@ -244,6 +250,10 @@ void tgcn_graph_destroy(tgcn_graph_t* g) {
   if (g->split_rows) cudaFree(g->split_rows);
   if (g->split_counters) cudaFree(g->split_counters);
   if (g->busy_event) cudaEventDestroy(g->busy_event);
+  if (g->host_in) cudaStreamDestroy(g->host_in);
+  if (g->host_out) cudaStreamDestroy(g->host_out);
+  for (auto e : g->host_ev)
+    if (e) cudaEventDestroy(e);
   delete g;
 }
 

@@ -49,7 +49,8 @@ struct SpmmArgs {
   const float* x_user;  // gather source: c < x_split ? x_user + c·d : x_item + (c - x_split)·d
   const float* x_item;
   int x_split;
-  int n_rows;
+  int n_rows;        // rows walked by this launch (all rows of the handle, or a row range: see RowRange)
+  int row_lo;        // first row of the range (0 for a whole launch); only used when `order` is NULL
   int n_units;       // row units of the group / slice kernels: n_rows, or the number of short rows when `order` is set
   const int* order;  // short rows (<= kSplitThreshold non-zeros) by decreasing step count, or NULL
   int d;
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
   } else {
     row = warp - a.n_segments;
     if (row >= a.n_rows) return;
+    row += a.row_lo;
     begin = __ldg(a.rowptr + row);
     end = __ldg(a.rowptr + row + 1);
     slot = -1;
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     // several rows share a warp when LPN < 32: `order` lists the short rows by decreasing step count so that
     // the lane groups of a warp finish together (ncu: 16 of 32 lanes active on the 16-wide slice without it)
     if (LPN < 32 && a.order) row = __ldg(a.order + row);
+    else row += a.row_lo;
     begin = __ldg(a.rowptr + row);
     end = __ldg(a.rowptr + row + 1);
     slot = -1;
@@ -473,6 +476,7 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.keep_div = 1.f;
   a.keep_scale = 1.f;
   a.n_rows = (int)g->n_rows;
+  a.row_lo = 0;
   a.order = g->order;  // NULL when the handle was created with the row order switched off (TGCN_ROW_ORDER=0 at creation)
   a.n_units = g->order ? g->n_ordered : (int)g->n_rows;
   a.d = (int)d;
@@ -488,6 +492,10 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.x_split = g->is_block ? 0x7fffffff : (int)g->n_users;
 }
 
+struct RowRange {  // a launch restricted to rows [row_lo, row_hi) (natural order) + the long-row segments [seg_lo, seg_hi)
+  int row_lo, row_hi, seg_lo, seg_hi;
+};
+
 struct ScatterSpec {  // destination of the last pass in feature-sliced mode (see Epilogue)
   int n_peers, users_per_rank, d_full, col_off;
   float* const* peer_user;
@@ -502,7 +510,7 @@ static int spmm_ex_impl(const tgcn_graph_t* g, int64_t d, const float* d_x_user,
                         const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
                         const float* const* h_add_user, const float* const* h_add_item, float divisor,
                         int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream,
-                        const ScatterSpec* sc);
+                        const ScatterSpec* sc, const RowRange* range = nullptr);
 
 extern "C" {
 
@@ -529,7 +537,7 @@ static int spmm_ex_impl(const tgcn_graph_t* g, int64_t d, const float* d_x_user,
                         const uint8_t* d_keep, float dropout, int32_t transposed, int32_t n_add,
                         const float* const* h_add_user, const float* const* h_add_item, float divisor,
                         int32_t accumulate, float* d_y, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream,
-                        const ScatterSpec* sc) {
+                        const ScatterSpec* sc, const RowRange* range) {
   if (int rc = check_common(g, d, 1)) return rc;
   TGCN_REQUIRE(d_x_user && (d_y || sc), "NULL x or y");
   TGCN_REQUIRE(n_add >= 0 && n_add <= kMaxAddends, "n_add=%d out of range", n_add);
@@ -574,6 +582,16 @@ static int spmm_ex_impl(const tgcn_graph_t* g, int64_t d, const float* d_x_user,
       a.ep.peer_user[q] = sc->peer_user[q];
       a.ep.peer_item[q] = sc->peer_item[q];
     }
+  }
+  if (range) {  // the partial-sum slots and split counters stay indexed globally; only the unit list shrinks
+    TGCN_REQUIRE(range->row_lo >= 0 && range->row_lo <= range->row_hi && range->row_hi <= g->n_rows && range->seg_lo >= 0 &&
+                     range->seg_lo <= range->seg_hi && range->seg_hi <= g->n_segments, "bad row range");
+    a.order = nullptr;
+    a.row_lo = range->row_lo;
+    a.n_rows = a.n_units = range->row_hi - range->row_lo;
+    a.segments = g->segments + range->seg_lo;
+    a.n_segments = range->seg_hi - range->seg_lo;
+    if (a.n_rows + a.n_segments == 0) return 0;
   }
   return launch_spmm(g, a, (cudaStream_t)stream);
 }
@@ -745,19 +763,114 @@ int tgcn_propagate_bwd(tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t sin
   return 0;
 }
 
-int tgcn_propagate_host(const tgcn_graph_t* g, int64_t d, int32_t n_layers, int32_t single, const float* h_user_w,
+// Host-buffer form of `representation`, pipelined over PCIe (full duplex) and three streams:
+//   copy-in stream : item table (the small one) first, then the user table in row chunks;
+//   `stream`       : layer 1's USER-row pass starts as soon as the item table has landed (user rows only gather item
+//                    rows — Â is bipartite) and overlaps the upload of the user table; the item-row pass waits for it;
+//                    layers 2..L-1 as usual; the LAST layer runs its item-row pass first, then the user rows in row
+//                    chunks (natural row order), each chunk signalling an event;
+//   copy-out stream: the item rows of the result, then every user-row chunk as soon as its launch has finished, so the
+//                    download overlaps the rest of the last layer.
+// `stream` finally waits for the last download, so the call keeps its stream-ordered contract.  The floor is the PCIe
+// time of the two tables (they cannot overlap each other: the result needs every layer): see DESIGN.md §4.
+constexpr int kHostChunks = 8;
+
+int tgcn_propagate_host(const tgcn_graph_t* cg, int64_t d, int32_t n_layers, int32_t single, const float* h_user_w,
                         const float* h_item_w, float* h_out, float* d_stage, void* d_workspace, int64_t workspace_bytes,
                         tgcn_stream_t stream) {
-  if (int rc = check_common(g, d, n_layers)) return rc;
+  if (int rc = check_common(cg, d, n_layers)) return rc;
   TGCN_REQUIRE(h_user_w && h_item_w && h_out && d_stage, "NULL buffer");
+  TGCN_REQUIRE(!cg->is_block, "propagate_host needs a whole-graph handle");
+  tgcn_graph* g = const_cast<tgcn_graph*>(cg);
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t nu = g->n_users * d, ni = g->n_items * d;
-  TGCN_CHECK_CUDA(cudaMemcpyAsync(d_stage, h_user_w, sizeof(float) * nu, cudaMemcpyHostToDevice, s));
-  TGCN_CHECK_CUDA(cudaMemcpyAsync(d_stage + nu, h_item_w, sizeof(float) * ni, cudaMemcpyHostToDevice, s));
+  const int64_t NU = g->n_users, NI = g->n_items, N = NU + NI;
+  const int64_t nu = NU * d, ni = NI * d;
+  float* e0_u = d_stage;
+  float* e0_i = d_stage + nu;
   float* d_out = d_stage + nu + ni;
-  if (int rc = tgcn_propagate_fwd(g, d, n_layers, single, d_stage, d_stage + nu, nullptr, 0.f, d_out, d_workspace, workspace_bytes, stream))
-    return rc;
-  TGCN_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(float) * (nu + ni), cudaMemcpyDeviceToHost, s));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  TGCN_CHECK_CUDA(cudaStreamIsCapturing(s, &cap));
+  if (n_layers == 0 || !g->bipartite || cap != cudaStreamCaptureStatusNone) {  // nothing to overlap / not splittable: serial form
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(e0_u, h_user_w, sizeof(float) * nu, cudaMemcpyHostToDevice, s));
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(e0_i, h_item_w, sizeof(float) * ni, cudaMemcpyHostToDevice, s));
+    if (int rc = tgcn_propagate_fwd(g, d, n_layers, single, e0_u, e0_i, nullptr, 0.f, d_out, d_workspace, workspace_bytes, stream)) return rc;
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(float) * (nu + ni), cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
+  if (!g->host_in) {
+    TGCN_CHECK_CUDA(cudaStreamCreateWithFlags(&g->host_in, cudaStreamNonBlocking));
+    TGCN_CHECK_CUDA(cudaStreamCreateWithFlags(&g->host_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostChunks + 5; ++i) TGCN_CHECK_CUDA(cudaEventCreateWithFlags(&g->host_ev[i], cudaEventDisableTiming));
+  }
+  cudaEvent_t ev_start = g->host_ev[kHostChunks], ev_items = g->host_ev[kHostChunks + 1], ev_users = g->host_ev[kHostChunks + 2],
+              ev_done = g->host_ev[kHostChunks + 3], ev_items_out = g->host_ev[kHostChunks + 4];
+  // ---- upload: ordered behind whatever `stream` did before (the staging buffers may still be in use) ----
+  TGCN_CHECK_CUDA(cudaEventRecord(ev_start, s));
+  TGCN_CHECK_CUDA(cudaStreamWaitEvent(g->host_in, ev_start, 0));
+  TGCN_CHECK_CUDA(cudaMemcpyAsync(e0_i, h_item_w, sizeof(float) * ni, cudaMemcpyHostToDevice, g->host_in));
+  TGCN_CHECK_CUDA(cudaEventRecord(ev_items, g->host_in));
+  for (int c = 0; c < kHostChunks; ++c) {  // chunked so that the copy engine never holds one multi-GB descriptor
+    const int64_t r0 = NU * c / kHostChunks, r1 = NU * (c + 1) / kHostChunks;
+    if (r1 > r0) TGCN_CHECK_CUDA(cudaMemcpyAsync(e0_u + r0 * d, h_user_w + r0 * d, sizeof(float) * (r1 - r0) * d, cudaMemcpyHostToDevice, g->host_in));
+  }
+  TGCN_CHECK_CUDA(cudaEventRecord(ev_users, g->host_in));
+  // ---- layers ----
+  const int64_t need = tgcn_propagate_workspace_bytes(g, d, n_layers);
+  TGCN_REQUIRE(workspace_bytes >= need && (d_workspace || need == 0), "workspace too small: need %lld bytes, got %lld", (long long)need, (long long)workspace_bytes);
+  const int64_t layer_bytes = align_up(N * d * (int64_t)sizeof(float), 256);
+  char* ws = (char*)d_workspace;
+  float* partial = (float*)(ws + (int64_t)(n_layers - 1) * layer_bytes);
+  const int64_t partial_bytes = workspace_bytes - ((char*)partial - ws);
+  auto buf = [&](int i) { return (float*)(ws + (int64_t)i * layer_bytes); };
+  const RowRange users{0, (int)NU, 0, g->n_user_segments}, items{(int)NU, (int)N, g->n_user_segments, g->n_segments};
+  const float* add_u[kMaxAddends];
+  const float* add_i[kMaxAddends];
+  for (int l = 1; l <= n_layers; ++l) {
+    const bool last = l == n_layers;
+    const float* xu = l == 1 ? e0_u : buf(l - 2);
+    const float* xi = l == 1 ? e0_i : nullptr;
+    int n_add = 0;
+    float divisor = 1.f;
+    if (last && !single) {
+      add_u[0] = e0_u;
+      add_i[0] = e0_i;
+      for (int t = 1; t < n_layers; ++t) {
+        add_u[t] = buf(t - 1);
+        add_i[t] = nullptr;
+      }
+      n_add = n_layers;
+      divisor = (float)(n_layers + 1);
+    }
+    float* y = last ? d_out : buf(l - 1);
+    auto pass = [&](const RowRange& r) {
+      return spmm_ex_impl(g, d, xu, xi, nullptr, 0.f, 0, n_add, add_u, add_i, divisor, 0, y, partial, partial_bytes, stream, nullptr, &r);
+    };
+    if (l == 1) TGCN_CHECK_CUDA(cudaStreamWaitEvent(s, ev_items, 0));
+    if (!last) {
+      if (int rc = pass(users)) return rc;                       // layer 1: overlaps the user-table upload
+      if (l == 1) TGCN_CHECK_CUDA(cudaStreamWaitEvent(s, ev_users, 0));
+      if (int rc = pass(items)) return rc;
+      continue;
+    }
+    // last layer: item rows first (their download starts at once), then the user rows chunk by chunk
+    if (l == 1) TGCN_CHECK_CUDA(cudaStreamWaitEvent(s, ev_users, 0));
+    if (int rc = pass(items)) return rc;
+    TGCN_CHECK_CUDA(cudaEventRecord(ev_items_out, s));
+    TGCN_CHECK_CUDA(cudaStreamWaitEvent(g->host_out, ev_items_out, 0));
+    TGCN_CHECK_CUDA(cudaMemcpyAsync(h_out + nu, d_out + nu, sizeof(float) * ni, cudaMemcpyDeviceToHost, g->host_out));
+    for (int c = 0; c < kHostChunks; ++c) {
+      const int64_t r0 = NU * c / kHostChunks, r1 = NU * (c + 1) / kHostChunks;
+      // the long user rows (segments) ride with chunk 0; they write rows of ANY chunk, all of which are downloaded after
+      // chunk 0's launch has finished (same stream, later events)
+      const RowRange chunk{(int)r0, (int)r1, c == 0 ? 0 : g->n_user_segments, g->n_user_segments};
+      if (int rc = pass(chunk)) return rc;
+      TGCN_CHECK_CUDA(cudaEventRecord(g->host_ev[c], s));
+      TGCN_CHECK_CUDA(cudaStreamWaitEvent(g->host_out, g->host_ev[c], 0));
+      if (r1 > r0) TGCN_CHECK_CUDA(cudaMemcpyAsync(h_out + r0 * d, d_out + r0 * d, sizeof(float) * (r1 - r0) * d, cudaMemcpyDeviceToHost, g->host_out));
+    }
+  }
+  TGCN_CHECK_CUDA(cudaEventRecord(ev_done, g->host_out));
+  TGCN_CHECK_CUDA(cudaStreamWaitEvent(s, ev_done, 0));
   return 0;
 }
 

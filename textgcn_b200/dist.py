@@ -183,6 +183,8 @@ class BipartitePropagator:
         self.part, self.rank, self.ug, self.ig, self.d, self.n_layers = part, rank, user_graph, item_graph, d, n_layers
         self.item_chunks = item_chunks or [(0, part.n_items, item_graph)]
         self.group, self.spmm_fn, self.mean_fn = group, spmm_fn, mean_fn
+        self.tail_fn = None  # optional hook (works, (addends, divisor), out_item) replacing the final wait + mean
+        self.comm = None     # optional C-ABI communicator (CabiComm): the per-hop all-reduce through tgcn_allreduce_sum_f32
         u0, u1 = part.users(rank)
         self.n_local = u1 - u0
         self.ubufs = [torch.empty((self.n_local, d), dtype=torch.float32, device=device) for _ in range(max(n_layers - 1, 0))]
@@ -205,7 +207,10 @@ class BipartitePropagator:
             for r0, r1, handle in self.item_chunks:
                 spmm(handle, src_u, dst[r0:r1], [], 1.0)
                 if ws > 1 and probe != "nocomm":
-                    works.append(dist.all_reduce(dst[r0:r1], group=self.group, async_op=True))
+                    if self.comm is not None:
+                        works.append(self.comm.all_reduce_async(dst[r0:r1]))
+                    else:
+                        works.append(dist.all_reduce(dst[r0:r1], group=self.group, async_op=True))
             return works
 
         # Software pipeline: the all-reduce of layer l's item table (AR_l) only feeds the USER rows of layer l+1, so it
@@ -222,12 +227,17 @@ class BipartitePropagator:
             else:
                 spmm(self.ug, cur_i, self.ubufs[layer - 1], [], 1.0)
                 nxt = item_partials(self.ubufs[layer - 1], self.ibufs[layer])   # B_{l+1}; AR_{l+1} queues behind AR_l
+            if last and self.tail_fn is not None:
+                # the item table's layer mean only needs AR_L, not the last user pass A_L: hand both to the owner's hook,
+                # which runs the mean on a side stream so that it overlaps A_L (GridPropagator._tail)
+                self.tail_fn(works, ([self.ibufs[L - 1]], 1.0) if single else ([e0_item] + self.ibufs, float(L + 1)), out_item)
+                return out_user_local, out_item
             for wk in works:
                 wk.wait()                                                   # item table of layer l is complete
             works = nxt
             cur_i = self.ibufs[layer - 1]
         if single:
-            out_item.copy_(cur_i)
+            self.mean_fn([cur_i], out_item, 1.0)
         else:
             self.mean_fn([e0_item] + self.ibufs, out_item, float(L + 1))
         return out_user_local, out_item
@@ -241,16 +251,25 @@ class _ResultTables:
     def __init__(self, per: int, n_items: int, d: int, world_size: int, rank: int, device, group, p2p: bool):
         self.world_size, self.group, self.p2p = world_size, group, p2p
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self._peer_flags, self._epoch, self._rank = None, 0, rank
         rows = max(per, 1)
         if p2p:
             from . import ops
+            self._ops = ops
             self.buf_u = ops.PeerBuffer(rows * d * 4, device)
             self.buf_i = ops.PeerBuffer(n_items * d * 4, device)
+            self.buf_f = ops.PeerBuffer(256, device)   # barrier flags: one int64 epoch slot per rank
+            self.buf_f.tensor((64,)).zero_()
+            torch.cuda.synchronize(device)
             handles = [None] * world_size
             if world_size > 1:
-                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle), group=group)
+                dist.all_gather_object(handles, (self.buf_u.handle, self.buf_i.handle, self.buf_f.handle), group=group)
             self.peer_u = [self.buf_u.ptr if q == rank else self.buf_u.open_peer(handles[q][0]) for q in range(world_size)]
             self.peer_i = [self.buf_i.ptr if q == rank else self.buf_i.open_peer(handles[q][1]) for q in range(world_size)]
+            # one process per GPU (NCCL): flag handshake in peer memory.  Processes SHARING a device (the gloo test) would
+            # spin against each other's time slices: they keep the collective barrier.
+            if world_size > 1 and dist.get_backend(group) == "nccl" and os.environ.get("TGCN_PEER_BARRIER", "1") != "0":
+                self._peer_flags = [self.buf_f.ptr if q == rank else self.buf_f.open_peer(handles[q][2]) for q in range(world_size)]
             self.out_u = self.buf_u.tensor((rows, d))
             self.out_i = self.buf_i.tensor((n_items, d))
         else:
@@ -258,14 +277,22 @@ class _ResultTables:
             self.out_i = torch.empty((n_items, d), dtype=torch.float32, device=device)
 
     def barrier(self) -> None:
-        """Stream-ordered barrier: returns (on the stream) once every rank's earlier work on its stream is complete."""
-        if self.world_size > 1:
+        """Stream-ordered barrier: returns (on the stream) once every rank's earlier work on its stream is complete.
+        p2p tables: a flag handshake in peer memory (one tiny kernel: every rank stores the barrier's epoch into its slot of
+        every peer's flag array and spins on its own array, tgcn_peer_barrier); otherwise a 1-float all-reduce."""
+        if self.world_size <= 1:
+            return
+        if self.p2p and self._peer_flags is not None:
+            self._epoch += 1
+            self._ops.peer_barrier(self._peer_flags, self._rank, self._epoch)
+        else:
             dist.all_reduce(self._flag, group=self.group)
 
     def close(self) -> None:
         if self.p2p:
             self.buf_u.close()
             self.buf_i.close()
+            self.buf_f.close()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -398,12 +425,21 @@ class GridPropagator:
     all-to-all / all-gather on ``group`` (the comparison arm, and what the gloo test drives on CPU)."""
 
     def __init__(self, part: GridPartition, rank: int, user_graph, item_graph, n_layers: int, device, row_group=None,
-                 group=None, exchange: str = "p2p", spmm_fn: Callable = _default_spmm, mean_fn: Callable = _default_mean):
+                 group=None, exchange: str = "p2p", spmm_fn: Callable = _default_spmm, mean_fn: Callable = _default_mean,
+                 comm=None):
         self.part, self.rank, self.group, self.exchange = part, rank, group, exchange
         self.g, self.r = part.coords(rank)
         self._spmm_fn, self._mean_fn = spmm_fn, mean_fn
         self.inner = BipartitePropagator(part.rows, self.r, user_graph, item_graph, part.ds, n_layers, device, group=row_group,
                                          spmm_fn=self._spmm, mean_fn=self._mean)
+        self.inner.comm = comm
+        self._side = None
+        if exchange == "p2p" and torch.device(device).type == "cuda" and os.environ.get("TGCN_GRID_SIDE_STREAM", "1") != "0":
+            # the item table's layer mean + broadcast runs beside the last user pass instead of behind it
+            self._side = torch.cuda.Stream(device=device)
+            self._ev_main = torch.cuda.Event()
+            self._ev_side = torch.cuda.Event()
+            self.inner.tail_fn = self._tail
         self.ug = user_graph
         P, d = part.world_size, part.d
         f0, f1 = part.final_users(rank)
@@ -470,18 +506,29 @@ class GridPropagator:
             return None
         return self._mean_fn(addends, self.loc_i, divisor)
 
+    def _tail(self, works, mean_args, out_item):
+        """Last layer: the item table's layer mean (+ its broadcast into every rank's replica) needs the final all-reduce
+        but not the last user pass, which is already enqueued on the main stream — run it on the side stream."""
+        main = torch.cuda.current_stream()
+        self._ev_main.record(main)          # everything the mean reads except AR_L was produced before this point
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_main)
+            for wk in works:
+                wk.wait()                   # the side stream (not the main one) waits for the collective
+            self._mean(mean_args[0], out_item, mean_args[1])
+            self._ev_side.record(self._side)
+        main.wait_event(self._ev_side)      # joins before the closing barrier
+
     def propagate(self, e0_user_slice_local: torch.Tensor, e0_item_slice: torch.Tensor, single: bool = False):
         """e0_user_slice_local: rows of this rank's row-group users, columns of its slice (n_local, d/G); e0_item_slice:
         (n_items, d/G).  Returns (users_emb rows [rank·per, ...) (n_final, d), items_emb (n_items, d))."""
         part, P = self.part, self.part.world_size
         if self.exchange == "p2p":
             self._timed("barrier", self.tables.barrier)  # every rank is done reading the previous result tables
-            if single:
-                raise NotImplementedError("single-layer output is not wired through the p2p exchange")
-            self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self._tok_i, single=False)
+            self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self._tok_i, single=single)
             self._timed("barrier", self.tables.barrier)  # every rank's stores have landed
             return self.out_u[:self.n_final], self.out_i
-        self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self.loc_i if single else self._tok_i, single=single)
+        self.inner.propagate(e0_user_slice_local, e0_item_slice, self._tok_u, self._tok_i, single=single)
         ds, ni = part.ds, part.n_items
         me0, me1 = part.final_users(self.rank)
 
@@ -520,6 +567,55 @@ class GridPropagator:
         self.tables.close()
 
 
+class CabiComm:
+    """An NCCL communicator owned through the C ABI (``tgcn_comm_*``): what a consumer of libtgcn_b200 that does not run
+    torch.distributed uses for the path's two exchanges — the per-hop all-reduce of the item-table slice and the
+    all-to-all of partial top-k tables.  The 128-byte unique id travels through any transport (here: a torch.distributed
+    object broadcast inside ``group``).  Collectives are enqueued on this object's own high-priority stream and ordered
+    with CUDA events, like torch's async NCCL work objects (``all_reduce_async(...).wait()``)."""
+
+    class _Work:
+        def __init__(self, event):
+            self.event = event
+
+        def wait(self):
+            torch.cuda.current_stream().wait_event(self.event)
+
+    def __init__(self, ranks: Sequence[int], rank: int, device, group=None):
+        from . import ops
+        self._ops = ops
+        self.ranks, self.rank, self.device = list(ranks), rank, torch.device(device)
+        me = self.ranks.index(rank)
+        uid = [ops.comm_unique_id() if me == 0 else None]
+        dist.broadcast_object_list(uid, src=self.ranks[0], group=group)
+        with torch.cuda.device(self.device):
+            self.handle = ops.comm_init_rank(len(self.ranks), me, uid[0])
+            self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+
+    def all_reduce_async(self, t: torch.Tensor):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self._ops.comm_allreduce_sum(self.handle, t, self.stream.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return CabiComm._Work(done)
+
+    def topk_exchange(self, part_ids: torch.Tensor, part_scores: torch.Tensor):
+        """All-to-all of the partial (n_ranks·rows, k) top-k tables on the current stream (tgcn_topk_exchange)."""
+        recv_ids, recv_sc = torch.empty_like(part_ids), torch.empty_like(part_scores)
+        self._ops.comm_topk_exchange(self.handle, len(self.ranks), part_ids, part_scores, recv_ids, recv_sc,
+                                     torch.cuda.current_stream().cuda_stream)
+        return recv_ids, recv_sc
+
+    def close(self):
+        if self.handle:
+            torch.cuda.synchronize(self.device)
+            self._ops.comm_destroy(self.handle)
+            self.handle = None
+
+
 def item_shard(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
     per = (n_items + world_size - 1) // world_size
     return min(rank * per, n_items), min((rank + 1) * per, n_items)
@@ -538,7 +634,7 @@ def _default_merge(mask_graph, part_ids, part_scores, users):
 
 def sharded_eval_topk(mask_graph, user_vecs: torch.Tensor, item_vecs: torch.Tensor, users: torch.Tensor, k: int,
                       rank: int, world_size: int, group=None, gather: bool = False, by_position: bool = False,
-                      rank_fn: Callable = _default_rank, merge_fn: Callable = _default_merge):
+                      rank_fn: Callable = _default_rank, merge_fn: Callable = _default_merge, comm: Optional["CabiComm"] = None):
     """Item-sharded full ranking with a cross-GPU top-k merge.
 
     ``users`` (int32 ids, identical on every rank; its length must be a multiple of world_size) are ranked by every
@@ -555,7 +651,9 @@ def sharded_eval_topk(mask_graph, user_vecs: torch.Tensor, item_vecs: torch.Tens
     per = n_users_ranked // world_size
     recv_ids = torch.empty_like(part_ids)
     recv_sc = torch.empty_like(part_sc)
-    if world_size > 1:
+    if world_size > 1 and comm is not None:
+        recv_ids, recv_sc = comm.topk_exchange(part_ids.contiguous(), part_sc.contiguous())
+    elif world_size > 1:
         dist.all_to_all_single(recv_ids, part_ids.contiguous(), group=group)
         dist.all_to_all_single(recv_sc, part_sc.contiguous(), group=group)
     else:

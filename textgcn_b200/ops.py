@@ -285,6 +285,61 @@ class PeerBuffer:
                 self.ptr = 0
 
 
+def peer_barrier(peer_flag_ptrs: Sequence[int], rank: int, epoch: int) -> None:
+    """Stream-ordered barrier over peer-mapped flag arrays (tgcn_peer_barrier) on the current stream."""
+    lib = _lib.load()
+    n = len(peer_flag_ptrs)
+    arr = (ctypes.c_void_p * n)(*peer_flag_ptrs)
+    check(lib.tgcn_peer_barrier(n, int(rank), arr, int(epoch), _stream()))
+
+
+def comm_unique_id() -> bytes:
+    lib = _lib.load()
+    buf = (ctypes.c_uint8 * 128)()
+    check(lib.tgcn_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return bytes(buf)
+
+
+def comm_init_rank(n_ranks: int, rank: int, uid: bytes) -> int:
+    """ncclCommInitRank on the current device through the C ABI; returns the communicator as an integer handle."""
+    lib = _lib.load()
+    comm = ctypes.c_void_p()
+    buf = (ctypes.c_uint8 * 128).from_buffer_copy(uid)
+    check(lib.tgcn_comm_init_rank(ctypes.byref(comm), n_ranks, rank, ctypes.cast(buf, ctypes.c_void_p)))
+    return int(comm.value)
+
+
+def comm_destroy(comm: int) -> None:
+    check(_lib.load().tgcn_comm_destroy(comm))
+
+
+def comm_allreduce_sum(comm: int, t: torch.Tensor, stream: Optional[int] = None) -> None:
+    """In-place sum of a contiguous fp32 tensor over the communicator, on ``stream`` (default: the current stream)."""
+    _chk(t, torch.float32, "tensor", align=4)
+    with torch.cuda.device(t.device):
+        check(_lib.load().tgcn_allreduce_sum_f32(comm, t.data_ptr(), t.numel(), _stream() if stream is None else stream))
+
+
+def comm_allgather(comm: int, send: torch.Tensor, recv: torch.Tensor, stream: Optional[int] = None) -> None:
+    _chk(send, torch.float32, "send", align=4)
+    _chk(recv, torch.float32, "recv", align=4)
+    with torch.cuda.device(send.device):
+        check(_lib.load().tgcn_allgather_f32(comm, send.data_ptr(), recv.data_ptr(), send.numel(), _stream() if stream is None else stream))
+
+
+def comm_topk_exchange(comm: int, n_ranks: int, part_ids, part_scores, recv_ids, recv_scores, stream: Optional[int] = None) -> None:
+    """All-to-all of partial top-k tables shaped (n_ranks · rows_per_rank, k) (tgcn_topk_exchange)."""
+    for t, dt, n in ((part_ids, torch.int32, "part_ids"), (recv_ids, torch.int32, "recv_ids"), (part_scores, torch.float32, "part_scores"),
+                     (recv_scores, torch.float32, "recv_scores")):
+        _chk(t, dt, n, 2, align=4)
+    rows, k = part_ids.shape
+    if rows % n_ranks:
+        raise _lib.TgcnError("the partial tables must hold a multiple of n_ranks rows")
+    with torch.cuda.device(part_ids.device):
+        check(_lib.load().tgcn_topk_exchange(comm, n_ranks, rows // n_ranks, k, part_ids.data_ptr(), part_scores.data_ptr(),
+                                             recv_ids.data_ptr(), recv_scores.data_ptr(), _stream() if stream is None else stream))
+
+
 def spmm_scatter(g: Graph, x: torch.Tensor, addends: Sequence[torch.Tensor], divisor: float, d_full: int, col_off: int,
                  users_per_rank: int, peer_user_ptrs: Sequence[int], peer_item_ptrs: Sequence[int]) -> None:
     """One SpMM pass (row-block or whole-graph handle, contiguous operands) whose result rows are stored into the peers'

@@ -722,15 +722,18 @@ def main():
             h_u = torch.empty_like(e0_u, device="cpu").pin_memory().copy_(e0_u.cpu())
             h_i = torch.empty_like(e0_i, device="cpu").pin_memory().copy_(e0_i.cpu())
             h_ou = torch.empty((f1 - f0, d), dtype=torch.float32).pin_memory()
-            h_oi = torch.empty((ni, d), dtype=torch.float32).pin_memory()
+            # items_emb is replicated after the exchange: every rank returns 1/P of it (round 1 copied all of it from every rank)
+            i0, i1 = tdist.item_shard(ni, world, rank)
+            h_oi = torch.empty((i1 - i0, d), dtype=torch.float32).pin_memory()
             d_u, d_i = torch.empty_like(e0_u), torch.empty_like(e0_i)
+            rows_out = (f1 - f0) + (i1 - i0)
 
             def e2e_step():
                 d_u.copy_(h_u, non_blocking=True)
                 d_i.copy_(h_i, non_blocking=True)
                 ou, oi = prop.propagate(d_u, d_i)
                 h_ou.copy_(ou, non_blocking=True)
-                h_oi.copy_(oi, non_blocking=True)
+                h_oi.copy_(oi[i0:i1], non_blocking=True)
         elif args.mg_scheme == "rowblock":
             h_e0 = torch.empty_like(e0, device="cpu").pin_memory().copy_(e0.cpu())
             h_o = torch.empty_like(out_local, device="cpu").pin_memory()
@@ -763,9 +766,11 @@ def main():
             rows_local = n
         e2e = {"value": nnz * L / (float(e_ms) * 1e-3), "unit": "edges/s", "ms_per_step": float(e_ms),
                "h2d_bytes_per_step": (e0_u.numel() + e0_i.numel()) * 4 if (world > 1 and args.mg_scheme == "grid") else rows_local * d * 4,
-               "d2h_bytes_per_step": rows_local * d * 4,
-               "api": "tgcn_propagate_host (pinned host E0 -> device, L layers, result -> pinned host)" if world == 1
-               else "host-pinned E0 shard -> device, L hops with the collective, result shard -> pinned host"}
+               "d2h_bytes_per_step": (rows_out if (world > 1 and args.mg_scheme == "grid") else rows_local) * d * 4,
+               "api": "tgcn_propagate_host (pinned host tables -> device, L layers, result -> pinned host; uploads / downloads on copy "
+                      "streams overlapping the first / last layer)" if world == 1
+               else "host-pinned E0 shard -> device, L hops with the collective, result shard (own user rows + 1/P of the item table) "
+                    "-> pinned host; bytes are per rank"}
 
     # ---- eval leg: fused score + mask + top-k ----------------------------------------------------------------
     ev = None

@@ -34,18 +34,26 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every csrc/*.cu to an object and link the shared library.  Returns its path."""
+DEBUG_LIB_PATH = os.path.join(PKG_DIR, "libtgcn_b200_dbg.so")
+
+
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """Compile every csrc/*.cu to an object and link the shared library.  Returns its path.
+    ``debug``: the debug-assert flavour (-DTGCN_DEBUG_BOUNDS: every index a kernel dereferences is range-checked with a device
+    assert) as libtgcn_b200_dbg.so; load it with TGCN_B200_LIB=<path> (tests / tools only)."""
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(INCLUDE, "*.h")))
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR + ("_dbg" if debug else "")
+    lib_path = DEBUG_LIB_PATH if debug else LIB_PATH
+    flags = NVCC_FLAGS + (["-DTGCN_DEBUG_BOUNDS"] if debug else [])
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     objs, jobs = [], []
     for src in sources:
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj])
+            jobs.append([nvcc, *flags, "-c", src, "-o", obj])
 
     def run(cmd):
         if verbose:
@@ -56,10 +64,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
         list(pool.map(run, jobs))
-    if force or jobs or _stale(LIB_PATH, objs):
-        run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs, "-ldl"])
-    return LIB_PATH
+    if force or jobs or _stale(lib_path, objs):
+        run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path, *objs, "-ldl"])
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

@@ -16,7 +16,7 @@ constexpr int kAdvThreads = 256;
 constexpr int kMaxChunks = 4;  // d <= 512 with 32 lanes
 
 struct AdvArgs {
-  int n_users, d, batch, n_cand, p2, kmax;
+  int n_users, n_items, d, batch, n_cand, p2, kmax;
   const int* users;
   const int* cands;  // (batch, n_cand) item ids
   const float* emb;  // (N, d)
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kAdvThreads) adv_select_kernel(const AdvArgs a
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u = __ldg(a.users + b);
+  TGCN_DASSERT(u >= 0 && u < a.n_users);
   const int d4 = a.d >> 2;
   // lanes per candidate: smallest power of two >= d/4, capped at 32
   int lpn = 1;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(kAdvThreads) adv_select_kernel(const AdvArgs a
     float part = 0.f;
     if (c < a.n_cand) {
       const int item = __ldg(cand + c);
+      TGCN_DASSERT(item >= 0 && item < a.n_items);
       const float* ip = a.emb + (size_t)(a.n_users + item) * a.d;
 #pragma unroll
       for (int w = 0; w < kMaxChunks; ++w) {
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) ltr_pairwise_kernel(const LtrPairArgs a) 
   const int lane = threadIdx.x & 31;
   if (warp >= a.batch) return;
   const int u = __ldg(a.users + warp), it = __ldg(a.items + warp);
+  TGCN_DASSERT(u >= 0 && u < a.n_users && it >= 0);
   float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
   const float* ue = a.emb + (size_t)u * a.d;
   const float* ie = a.emb + (size_t)(a.n_users + it) * a.d;
@@ -253,6 +256,7 @@ int tgcn_adv_select(const tgcn_graph_t* mask_graph, int64_t d, int64_t batch, in
   TGCN_REQUIRE(d_users && d_cands && d_emb && d_out_negs && d_out_counts, "NULL argument");
   AdvArgs a;
   a.n_users = (int)mask_graph->n_users;
+  a.n_items = (int)mask_graph->n_items;
   a.d = (int)d;
   a.batch = (int)batch;
   a.n_cand = n_cand;

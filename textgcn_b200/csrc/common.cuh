@@ -29,6 +29,16 @@ void set_error(const char* fmt, ...);
 
 #define TGCN_CHECK_LAUNCH() TGCN_CHECK_CUDA(cudaGetLastError())
 
+// Debug-assert build (textgcn_b200/build.py --debug -> libtgcn_b200_dbg.so, selected with TGCN_B200_LIB): every index a
+// kernel dereferences is range-checked with a device assert.  compute-sanitizer is closed on this GPU pool, so the GPU
+// parity suite is run once per round against this build instead (profiles/r02/README.md).  Compiled out otherwise.
+#ifdef TGCN_DEBUG_BOUNDS
+#include <assert.h>
+#define TGCN_DASSERT(cond) assert(cond)
+#else
+#define TGCN_DASSERT(cond) ((void)0)
+#endif
+
 constexpr int kSplitThreshold = 128;  // rows longer than this are cut into segments
 constexpr int kSegmentLen = 64;       // nnz per segment of a long row
 
@@ -38,7 +48,9 @@ struct Segment {  // one warp's (or lane group's) share of a long row
   int end;
   int slot;       // index into the partial-sum scratch
   int split;      // index of the row in the split-row table
-  int pad[3];
+  int qbegin;     // the same range in the packed layout (quads of four non-zeros, see tgcn_graph::qptr)
+  int qend;
+  int pad;
 };
 struct SplitRow {
   int row;
@@ -59,6 +71,9 @@ struct tgcn_graph {
   const int* col;
   const float* val;
   int* tperm;  // owned, built on demand
+  int* qptr;      // owned: packed copy of the CSR for the SpMM kernels — row r owns quads [qptr[r], qptr[r+1]) of four
+  int4* qcol;     //        (col, val) pairs, rows padded to whole quads with col = the row's last column / val = 0 (8 B/nnz + padding; NULL when
+  float4* qval;   //        switched off with TGCN_SPMM_PACKED=0 at creation or when the allocation failed)
   tgcn::Segment* segments;
   int n_segments;
   tgcn::SplitRow* split_rows;

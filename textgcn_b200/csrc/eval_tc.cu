@@ -353,6 +353,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     const int m = m0 + t;
     const bool valid = m < a.n_rank;
     const int user = valid ? (a.users ? __ldg(a.users + m) : m) : 0;
+    TGCN_DASSERT(!valid || !a.mrowptr || user >= a.mrow_begin);
     int mlo = 0, mhi = 0;
     if (valid && a.mrowptr) {
       mlo = __ldg(a.mrowptr + user - a.mrow_begin);
@@ -406,6 +407,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           const uint32_t b = (uint32_t)item & 127u;
           const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
           const bool maybe = (word >> (b & 31)) & 1u;
+          TGCN_DASSERT(item >= a.item_begin && item < a.item_begin + a.n_range);
           if (!maybe || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
             reg_list_insert<KL>(ls, li, s, item);
             thr = ls[KL - 1];

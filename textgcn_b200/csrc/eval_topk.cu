@@ -81,6 +81,7 @@ __device__ __noinline__ void warp_list_insert(float* ls, int* li, int k, float s
 __device__ __forceinline__ bool is_masked(const EvalArgs& a, int user, int item) {
   if (a.mrowptr == nullptr) return false;
   const int r = user - a.mrow_begin;
+  TGCN_DASSERT(r >= 0 && item >= a.item_begin && item < a.item_end);
   return sorted_contains(a.mcol, __ldg(a.mrowptr + r), __ldg(a.mrowptr + r + 1), item + a.mcol_off);
 }
 

@@ -46,6 +46,30 @@ __global__ void transpose_perm_kernel(const int* __restrict__ rowptr, const int*
   }
 }
 
+// Packed copy of the CSR: one thread per quad; its row by binary search in qptr.
+__global__ void pack_quads_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                                  const int* __restrict__ qptr, int n_rows, int n_quads, int4* __restrict__ qcol, float4* __restrict__ qval) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_quads) return;
+  int lo = 0, hi = n_rows;  // largest r with qptr[r] <= q
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(qptr + mid) <= q) lo = mid;
+    else hi = mid;
+  }
+  const int p = __ldg(rowptr + lo) + 4 * (q - __ldg(qptr + lo)), end = __ldg(rowptr + lo + 1);
+  int c[4];
+  float v[4];
+  const int last = __ldg(col + end - 1);  // padding repeats the row's last column with weight 0: gathers stay unconditional
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c[i] = p + i < end ? __ldg(col + p + i) : last;
+    v[i] = p + i < end ? __ldg(val + p + i) : 0.f;
+  }
+  qcol[q] = make_int4(c[0], c[1], c[2], c[3]);
+  qval[q] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // Per row: columns strictly increasing (the binary searches rely on it) and, for a whole graph, on the other
 // side of the user/item boundary.  flags[0] |= unsorted, flags[1] |= not bipartite.
 __global__ void check_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_rows, int n_users,
@@ -88,19 +112,52 @@ static int build_segments(tgcn_graph* g, cudaStream_t stream) {
                rowptr[0], rowptr[g->n_rows], (long long)g->nnz);
   std::vector<Segment> segs;
   std::vector<SplitRow> splits;
+  std::vector<int> qptr(g->n_rows + 1);
+  int64_t n_quads = 0;
   int max_deg = 0;
   for (int64_t r = 0; r < g->n_rows; ++r) {
     const int deg = rowptr[r + 1] - rowptr[r];
     TGCN_REQUIRE(deg >= 0, "rowptr is not non-decreasing at row %lld", (long long)r);
     if (deg > max_deg) max_deg = deg;
+    qptr[r] = (int)n_quads;
     if (deg > kSplitThreshold) {
       SplitRow sr{(int)r, (int)segs.size(), 0, 0};
       for (int b = rowptr[r]; b < rowptr[r + 1]; b += kSegmentLen) {
         int e = b + kSegmentLen < rowptr[r + 1] ? b + kSegmentLen : rowptr[r + 1];
-        segs.push_back(Segment{(int)r, b, e, (int)segs.size(), (int)splits.size(), {0, 0, 0}});
+        const int qb = (int)n_quads + (b - rowptr[r]) / 4, qe = (int)n_quads + (e - rowptr[r] + 3) / 4;  // kSegmentLen % 4 == 0
+        segs.push_back(Segment{(int)r, b, e, (int)segs.size(), (int)splits.size(), qb, qe, 0});
         sr.n_parts++;
       }
       splits.push_back(sr);
+    }
+    n_quads += (deg + 3) / 4;
+    TGCN_REQUIRE(n_quads < (1ll << 31), "packed layout exceeds int32 indexing");
+  }
+  qptr[g->n_rows] = (int)n_quads;
+  {
+    // Packed copy for the SpMM kernels (A/B switch, read once per handle: TGCN_SPMM_PACKED=0 keeps the 32-bit col/val loads).
+    // Failing to allocate it is not an error: the kernels then read the borrowed CSR arrays.
+    const char* sw = getenv("TGCN_SPMM_PACKED");
+    if (n_quads > 0 && !(sw && atoi(sw) == 0)) {
+      bool ok = cudaMalloc(&g->qptr, sizeof(int) * qptr.size()) == cudaSuccess && cudaMalloc(&g->qcol, sizeof(int4) * n_quads) == cudaSuccess &&
+                cudaMalloc(&g->qval, sizeof(float4) * n_quads) == cudaSuccess;
+      if (ok) {
+        ok = cudaMemcpyAsync(g->qptr, qptr.data(), sizeof(int) * qptr.size(), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+        if (ok) {
+          pack_quads_kernel<<<(unsigned)((n_quads + 255) / 256), 256, 0, stream>>>(g->rowptr, g->col, g->val, g->qptr, (int)g->n_rows,
+                                                                                   (int)n_quads, g->qcol, g->qval);
+          ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess;  // qptr (host vector) dies with this scope
+        }
+      }
+      if (!ok) {
+        (void)cudaGetLastError();
+        if (g->qptr) cudaFree(g->qptr);
+        if (g->qcol) cudaFree(g->qcol);
+        if (g->qval) cudaFree(g->qval);
+        g->qptr = nullptr;
+        g->qcol = nullptr;
+        g->qval = nullptr;
+      }
     }
   }
   // processing order of the short rows: stable counting sort by (user/item phase, steps descending)
@@ -178,6 +235,9 @@ static int create_common(tgcn_graph_t** out, int64_t n_users, int64_t n_items, i
   g->col = d_col;
   g->val = d_val;
   g->tperm = nullptr;
+  g->qptr = nullptr;
+  g->qcol = nullptr;
+  g->qval = nullptr;
   g->order = nullptr;
   g->n_ordered = 0;
   g->segments = nullptr;
@@ -245,6 +305,9 @@ int tgcn_graph_build_transpose_perm(tgcn_graph_t* g, tgcn_stream_t stream) {
 void tgcn_graph_destroy(tgcn_graph_t* g) {
   if (!g) return;
   if (g->tperm) cudaFree(g->tperm);
+  if (g->qptr) cudaFree(g->qptr);
+  if (g->qcol) cudaFree(g->qcol);
+  if (g->qval) cudaFree(g->qval);
   if (g->order) cudaFree(g->order);
   if (g->segments) cudaFree(g->segments);
   if (g->split_rows) cudaFree(g->split_rows);

@@ -42,6 +42,9 @@ struct SpmmArgs {
   const int* rowptr;
   const int* col;
   const float* val;
+  const int* qptr;      // packed layout (handle-owned, NULL = not built): row r owns quads [qptr[r], qptr[r+1]) ...
+  const int4* qcol;     // ... of four column ids (padding past the row end repeats the row's last column) ...
+  const float4* qval;   // ... and four values (0 on padding): two 128-bit loads per four non-zeros instead of eight 32-bit ones
   const uint8_t* keep;  // per-nnz keep mask or NULL
   const int* tperm;     // when set, entry p uses keep[tperm[p]] (transposed dropout matrix)
   float keep_div;       // survivors are divided by (1 - p) (generic kernel) ...
@@ -54,6 +57,8 @@ struct SpmmArgs {
   int n_units;       // row units of the group / slice kernels: n_rows, or the number of short rows when `order` is set
   const int* order;  // short rows (<= kSplitThreshold non-zeros) by decreasing step count, or NULL
   int d;
+  unsigned zero;  // always 0: an operand the compiler cannot fold (see TGCN_GATHER_FMA)
+  long long dbg_x_rows, dbg_nnz, dbg_rows;  // bounds for the debug-assert build: rows of the gather source, nnz and rows of the handle
   const Segment* segments;
   int n_segments;
   const SplitRow* split_rows;
@@ -85,6 +90,7 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int row, int c
     const int grow = row + ep.row_base;  // global row id (row blocks start at row_base)
     if (grow < ep.n_users) {
       const int q = grow / ep.users_per_rank;
+      TGCN_DASSERT(q >= 0 && q < ep.n_peers);
       *reinterpret_cast<float4*>(ep.peer_user[q] + (size_t)(grow - q * ep.users_per_rank) * ep.d_full + coff) = s;
     } else {
       const size_t o = (size_t)(grow - ep.n_users) * ep.d_full + coff;
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(256) spmm_rows_kernel(const SpmmArgs a) {
         vv[u] = __shfl_sync(0xffffffffu, v, idx & 31);
         const bool ok = idx < cnt;
         if (!ok) vv[u] = 0.f;
+        TGCN_DASSERT(!ok || (cc >= 0 && cc < a.dbg_x_rows));
         const float* xr = (cc < a.x_split ? a.x_user + (size_t)cc * a.d : a.x_item + (size_t)(cc - a.x_split) * a.d);
 #pragma unroll
         for (int w = 0; w < VPL; ++w) {
@@ -237,14 +244,19 @@ constexpr int kUnroll = 4;
 #ifndef TGCN_DEFAULT_LANES_D64
 #define TGCN_DEFAULT_LANES_D64 16
 #endif
+#ifndef TGCN_DEFAULT_QUADS_D64
+#define TGCN_DEFAULT_QUADS_D64 1
+#endif
 constexpr int kGroupThreads = 128;
 
-template <int LPN, int VPL>
+template <int LPN, int VPL, int QU, bool PACKED, bool MASKED>
 __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArgs a) {
   constexpr int D = 4 * LPN * VPL;
   const int tid = blockIdx.x * kGroupThreads + threadIdx.x;
   const int unit = tid / LPN, sub = tid % LPN;
+  constexpr bool packed = PACKED;
   int row, begin, end, slot, split = -1;
+  int qb = 0, qe = 0;  // packed: the quads of this unit
   if (unit < a.n_segments) {
     const Segment s = a.segments[unit];
     row = s.row;
@@ -252,6 +264,8 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     end = s.end;
     slot = s.slot;
     split = s.split;
+    qb = s.qbegin;
+    qe = s.qend;
   } else {
     row = unit - a.n_segments;
     if (row >= (LPN < 32 ? a.n_units : a.n_rows)) return;
@@ -259,54 +273,104 @@ __global__ void __launch_bounds__(kGroupThreads) spmm_group_kernel(const SpmmArg
     // the lane groups of a warp finish together (ncu: 16 of 32 lanes active on the 16-wide slice without it)
     if (LPN < 32 && a.order) row = __ldg(a.order + row);
     else row += a.row_lo;
-    begin = __ldg(a.rowptr + row);
-    end = __ldg(a.rowptr + row + 1);
     slot = -1;
-    if (end - begin > kSplitThreshold) return;  // handled as segments
+    if (packed) {
+      qb = __ldg(a.qptr + row);
+      qe = __ldg(a.qptr + row + 1);
+      if (qe - qb > kSplitThreshold / 4) return;  // handled as segments (deg > 128 <=> more than 32 quads)
+      begin = end = 0;
+      if (MASKED) begin = __ldg(a.rowptr + row);  // mask bytes are indexed by the ORIGINAL nnz position
+    } else {
+      begin = __ldg(a.rowptr + row);
+      end = __ldg(a.rowptr + row + 1);
+      if (end - begin > kSplitThreshold) return;  // handled as segments
+    }
   }
+  TGCN_DASSERT(row >= 0 && row < a.dbg_rows && qb <= qe && begin <= a.dbg_nnz);
   // Â is bipartite: user rows only reference item columns and vice versa, so the table select happens once
   // per row instead of once per gather (launch_spmm rejects a non-bipartite graph with split tables).
   const float* xb = ((a.x_split != 0x7fffffff && row < a.x_split) ? a.x_item - (size_t)a.x_split * D : a.x_user) + sub * 4;
   float4 acc[VPL];
 #pragma unroll
   for (int w = 0; w < VPL; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool masked = a.keep != nullptr;
-  // col/val of step p (c < 0: no gather — past the row end or a dropped edge)
-  auto load_cv = [&](int p, int (&c)[kUnroll], float (&v)[kUnroll]) {
+  constexpr bool masked = MASKED;
+  constexpr int NZ = 4 * QU;  // non-zeros in flight per lane and step
+  // dropped edges (c < 0: no gather at all) and the 1/(1-p) rescale; p = original position of c[0]
+  auto apply_mask = [&](int p, int (&c)[NZ], float (&v)[NZ]) {
 #pragma unroll
-    for (int i = 0; i < kUnroll; ++i) {
-      const bool ok = p + i < end;
-      c[i] = ok ? __ldg(a.col + p + i) : -1;
-      v[i] = ok ? __ldg(a.val + p + i) : 0.f;
-    }
-    if (masked) {
-#pragma unroll
-      for (int i = 0; i < kUnroll; ++i) {
-        if (c[i] >= 0) {
-          const int q = a.tperm ? __ldg(a.tperm + p + i) : p + i;
-          if (__ldg(a.keep + q) == 0) c[i] = -1;  // dropped edge: no gather at all
-          v[i] *= a.keep_scale;
-        }
+    for (int i = 0; i < NZ; ++i) {
+      if (c[i] >= 0) {
+        TGCN_DASSERT(p + i >= 0 && p + i < a.dbg_nnz);
+        const int q = a.tperm ? __ldg(a.tperm + p + i) : p + i;
+        TGCN_DASSERT(q >= 0 && q < a.dbg_nnz);
+        if (__ldg(a.keep + q) == 0) c[i] = -1;
+        v[i] *= a.keep_scale;
       }
     }
   };
-  // (Prefetching step p + 1's col/val ahead of step p's gathers was measured slower everywhere: 48 registers instead
-  // of 40 cost more occupancy than the shorter dependent chain returned — c5 120.2 -> 124.5 ms, c2 0.371 -> 0.392 ms.)
-  for (int p = begin; p < end; p += kUnroll) {
-    int c[kUnroll];
-    float v[kUnroll];
-    load_cv(p, c, v);
-    float4 x[kUnroll][VPL];
+// every gather of a step is issued before the first FMA of the step (NZ independent 128-bit loads in flight per lane); the
+// FMAs then run strictly in nnz order, so the per-row summation order never depends on the layout.  Written out in the loop
+// bodies (not as a lambda): ptxas otherwise interleaves load / FMA pairs through one register quad and serialises the gathers.
+  // packed + unmasked: the padding of a row repeats its last column with value 0, so every gather is unconditional
+  constexpr bool kSkip = !PACKED || MASKED;
+#define TGCN_GATHER_FMA(c, v)                                                                                          \
+  do {                                                                                                                 \
+    float4 x[NZ][VPL];                                                                                                 \
+    _Pragma("unroll") for (int i = 0; i < NZ; ++i) TGCN_DASSERT(c[i] >= (kSkip ? -1 : 0) && c[i] < a.dbg_x_rows);      \
+    _Pragma("unroll") for (int i = 0; i < NZ; ++i) _Pragma("unroll") for (int w = 0; w < VPL; ++w)                     \
+        x[i][w] = (kSkip && c[i] < 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(xb + (size_t)c[i] * D + w * (LPN * 4)); \
+    /* ptxas otherwise threads load / FMA pairs through one register quad and keeps 1-2 gathers in flight: make the   \
+       first weight depend on EVERY gathered row (OR with `all & a.zero`, a.zero == 0 at run time), so all NZ·VPL loads \
+       are issued before the first FMA.  Three logic instructions per step; values are unchanged. */                   \
+    unsigned all_bits = 0xffffffffu;                                                                                   \
+    _Pragma("unroll") for (int i = 0; i < NZ; ++i) _Pragma("unroll") for (int w = 0; w < VPL; ++w)                     \
+        all_bits &= __float_as_uint(x[i][w].x);                                                                        \
+    float v0 = __uint_as_float(__float_as_uint(v[0]) | (all_bits & a.zero));                                           \
+    _Pragma("unroll") for (int i = 0; i < NZ; ++i) _Pragma("unroll") for (int w = 0; w < VPL; ++w)                     \
+        fma4(acc[w], i == 0 ? v0 : v[i], x[i][w]);                                                                     \
+  } while (0)
+  if (packed) {
+    // ncu on the 32-bit col/val loads at d = 64: L1/TEX was the busiest unit (62 %) and half of its wavefronts were the
+    // group-uniform col/val words; one int4 + one float4 per four non-zeros cuts those eightfold and drops the per-element
+    // bounds predicates (padding carries c = -1).
+#pragma unroll 1
+    for (int q = qb; q < qe; q += QU) {
+      int c[NZ];
+      float v[NZ];
 #pragma unroll
-    for (int i = 0; i < kUnroll; ++i)
+      for (int u = 0; u < QU; ++u) {
+        const int qq = (QU == 1 || q + u < qe) ? q + u : q;  // odd tail of a two-quad step: re-read quad q with zero weights
+        const int4 cc = __ldg(a.qcol + qq);
+        float4 vv = __ldg(a.qval + qq);
+        if (QU > 1 && qq != q + u) vv = make_float4(0.f, 0.f, 0.f, 0.f);
+        c[4 * u + 0] = cc.x, c[4 * u + 1] = cc.y, c[4 * u + 2] = cc.z, c[4 * u + 3] = cc.w;
+        v[4 * u + 0] = vv.x, v[4 * u + 1] = vv.y, v[4 * u + 2] = vv.z, v[4 * u + 3] = vv.w;
+      }
+      if (masked) {
 #pragma unroll
-      for (int w = 0; w < VPL; ++w)
-        x[i][w] = c[i] < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(xb + (size_t)c[i] * D + w * (LPN * 4));
+        for (int i = 0; i < NZ; ++i)
+          if (v[i] == 0.f) c[i] = -1;  // padding (real entries of Â are positive): no mask byte belongs to it
+        apply_mask(begin + 4 * (q - qb), c, v);
+      }
+      TGCN_GATHER_FMA(c, v);
+    }
+  } else {
+    // (Prefetching step p + 1's col/val ahead of step p's gathers was measured slower everywhere: 48 registers instead
+    // of 40 cost more occupancy than the shorter dependent chain returned — c5 120.2 -> 124.5 ms, c2 0.371 -> 0.392 ms.)
+    for (int p = begin; p < end; p += NZ) {
+      int c[NZ];
+      float v[NZ];
 #pragma unroll
-    for (int i = 0; i < kUnroll; ++i)
-#pragma unroll
-      for (int w = 0; w < VPL; ++w) fma4(acc[w], v[i], x[i][w]);
+      for (int i = 0; i < NZ; ++i) {
+        const bool ok = p + i < end;
+        c[i] = ok ? __ldg(a.col + p + i) : -1;
+        v[i] = ok ? __ldg(a.val + p + i) : 0.f;
+      }
+      if (masked) apply_mask(p, c, v);
+      TGCN_GATHER_FMA(c, v);
+    }
   }
+#undef TGCN_GATHER_FMA
 #pragma unroll
   for (int w = 0; w < VPL; ++w) {
     const int chunk = sub + w * LPN;
@@ -379,10 +443,25 @@ __global__ void __launch_bounds__(256) layer_mean_scatter_kernel(const MeanScatt
 }
 
 template <int LPN, int VPL>
-static void launch_group(const SpmmArgs& a, cudaStream_t s) {
+static void launch_group(const SpmmArgs& a, cudaStream_t s, int quads) {
   const int64_t units = (int64_t)a.n_segments + (LPN < 32 ? a.n_units : a.n_rows);
   const int64_t blocks = (units * LPN + kGroupThreads - 1) / kGroupThreads;
-  spmm_group_kernel<LPN, VPL><<<(unsigned)blocks, kGroupThreads, 0, s>>>(a);
+  const bool packed = a.qptr != nullptr, masked = a.keep != nullptr;
+  constexpr int Q2 = VPL == 1 ? 2 : 1;  // two quads per step only for the one-float4-per-lane layouts (register budget)
+  const unsigned nb = (unsigned)blocks;
+#define TGCN_GROUP_LAUNCH(QU_, P_, M_) spmm_group_kernel<LPN, VPL, QU_, P_, M_><<<nb, kGroupThreads, 0, s>>>(a)
+  if (quads == 2 && Q2 == 2) {
+    if (packed && masked) TGCN_GROUP_LAUNCH(Q2, true, true);
+    else if (packed) TGCN_GROUP_LAUNCH(Q2, true, false);
+    else if (masked) TGCN_GROUP_LAUNCH(Q2, false, true);
+    else TGCN_GROUP_LAUNCH(Q2, false, false);
+  } else {
+    if (packed && masked) TGCN_GROUP_LAUNCH(1, true, true);
+    else if (packed) TGCN_GROUP_LAUNCH(1, true, false);
+    else if (masked) TGCN_GROUP_LAUNCH(1, false, true);
+    else TGCN_GROUP_LAUNCH(1, false, false);
+  }
+#undef TGCN_GROUP_LAUNCH
 }
 
 // Lane layout per width, read ONCE per process (A/B switches for profiling; the defaults are the measured best):
@@ -390,12 +469,15 @@ static void launch_group(const SpmmArgs& a, cudaStream_t s) {
 // float4 per lane, half the (group-redundant) col / val / address instructions per non-zero.
 struct SpmmTuning {
   int lanes_d64, lanes_d128;
+  int quads_d64, quads_d128;  // quads (4 non-zeros) in flight per lane and step: TGCN_SPMM_QUADS_D64 / _D128 = 1 | 2
 };
 static const SpmmTuning& spmm_tuning() {
   static const SpmmTuning t = [] {
-    SpmmTuning v{TGCN_DEFAULT_LANES_D64, 32};
+    SpmmTuning v{TGCN_DEFAULT_LANES_D64, 32, TGCN_DEFAULT_QUADS_D64, 1};
     if (const char* e = getenv("TGCN_SPMM_LANES_D64")) v.lanes_d64 = atoi(e) == 8 ? 8 : 16;
     if (const char* e = getenv("TGCN_SPMM_LANES_D128")) v.lanes_d128 = atoi(e) == 16 ? 16 : 32;
+    if (const char* e = getenv("TGCN_SPMM_QUADS_D64")) v.quads_d64 = atoi(e) == 2 ? 2 : 1;
+    if (const char* e = getenv("TGCN_SPMM_QUADS_D128")) v.quads_d128 = atoi(e) == 2 ? 2 : 1;
     return v;
   }();
   return t;
@@ -439,13 +521,13 @@ static int launch_spmm(const tgcn_graph* g, SpmmArgs& a, cudaStream_t s) {
   const bool contiguous = a.x_split == 0x7fffffff || a.x_item == a.x_user + (size_t)a.x_split * d;
   const bool group_ok = g->bipartite || contiguous;  // per-row table select needs a bipartite Â or one table
   const SpmmTuning& tune = spmm_tuning();
-  if (group_ok && d == 16) launch_group<4, 1>(a, s);
-  else if (group_ok && d == 32) launch_group<8, 1>(a, s);
-  else if (group_ok && d == 64 && tune.lanes_d64 == 8) launch_group<8, 2>(a, s);
-  else if (group_ok && d == 64) launch_group<16, 1>(a, s);
-  else if (group_ok && d == 128 && tune.lanes_d128 == 16) launch_group<16, 2>(a, s);
-  else if (group_ok && d == 128) launch_group<32, 1>(a, s);
-  else if (group_ok && d == 256) launch_group<32, 2>(a, s);
+  if (group_ok && d == 16) launch_group<4, 1>(a, s, 1);
+  else if (group_ok && d == 32) launch_group<8, 1>(a, s, tune.quads_d64);
+  else if (group_ok && d == 64 && tune.lanes_d64 == 8) launch_group<8, 2>(a, s, 1);
+  else if (group_ok && d == 64) launch_group<16, 1>(a, s, tune.quads_d64);
+  else if (group_ok && d == 128 && tune.lanes_d128 == 16) launch_group<16, 2>(a, s, 1);
+  else if (group_ok && d == 128) launch_group<32, 1>(a, s, tune.quads_d128);
+  else if (group_ok && d == 256) launch_group<32, 2>(a, s, 1);
   else if (d <= 16) spmm_rows_kernel<4, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
   else if (d <= 32) spmm_rows_kernel<8, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
   else if (d <= 64) spmm_rows_kernel<16, 1><<<(unsigned)blocks, threads, 0, s>>>(a);
@@ -471,11 +553,18 @@ static void base_args(const tgcn_graph* g, int64_t d, SpmmArgs& a) {
   a.rowptr = g->rowptr;
   a.col = g->col;
   a.val = g->val;
+  a.qptr = g->qptr;
+  a.qcol = g->qcol;
+  a.qval = g->qval;
   a.keep = nullptr;
   a.tperm = nullptr;
   a.keep_div = 1.f;
   a.keep_scale = 1.f;
   a.n_rows = (int)g->n_rows;
+  a.zero = 0u;
+  a.dbg_rows = g->n_rows;
+  a.dbg_nnz = g->nnz;
+  a.dbg_x_rows = g->is_block ? (1ll << 31) : g->n_users + g->n_items;  // a row block gathers from a caller-sized table
   a.row_lo = 0;
   a.order = g->order;  // NULL when the handle was created with the row order switched off (TGCN_ROW_ORDER=0 at creation)
   a.n_units = g->order ? g->n_ordered : (int)g->n_rows;

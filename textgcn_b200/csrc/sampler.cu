@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) sample_bpr_kernel(const SampleArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.batch) return;
   const int u = __ldg(a.users + b);
+  TGCN_DASSERT(u >= 0 && u < a.n_users);
   const int lo = __ldg(a.rowptr + u), hi = __ldg(a.rowptr + u + 1);
   const int deg = hi - lo;
   const unsigned long long key = a.seed ^ ((unsigned long long)(b + 1) * 0x9E3779B97F4A7C15ULL);

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TGCN_ABI_VERSION 1
+#define TGCN_ABI_VERSION 2
 #define TGCN_MAX_LAYERS 15
 #define TGCN_MAX_PEERS 8
 #define TGCN_MAX_TOPK 128
@@ -115,14 +115,18 @@ int tgcn_propagate_sliced(const tgcn_graph_t* g, int64_t d_slice, int32_t n_laye
 
 /* The two building blocks of the GRID scheme (feature slices x user partitions; textgcn_b200.dist.GridPropagator), where
  * the hops run through tgcn_spmm_ex on row-block handles and only the last pass changes layout:
- * spmm_scatter: one pass  (add_0 + ... + Â_block·X) / divisor  whose rows go to the peers' full-width tables exactly as in
- *   tgcn_propagate_sliced (global row id = the block's row_begin + local row);
+ * spmm_scatter: one pass  (add_0 + ... + Â_block·X) / divisor  whose rows go to the peers' full-width tables: user row u
+ *   (global id = the block's row_begin + local row) is stored at local row (u - user_row0) % users_per_rank of
+ *   h_peer_user_out[(u - user_row0) / users_per_rank] — with user_row0 = the first user of the rank's row partition and the
+ *   n_peers = G feature-slice partners of that partition, the rows never leave their row group (tgcn_propagate_sliced is the
+ *   user_row0 = 0, n_peers = P case); item rows go to every h_peer_item_out[q];
  * layer_mean_scatter: (add_0 + ... + add_{n_add-1}) / divisor over (n_rows, d_slice) tables, stored at column col_off of
  *   rows [row0, row0 + n_rows) of every h_dst[q] (d_full-wide) — the item table's layer mean and its all-gather in one. */
 int tgcn_spmm_scatter(const tgcn_graph_t* g, int64_t d_slice, const float* d_x_user, const float* d_x_item, int32_t n_add,
                       const float* const* h_add_user, const float* const* h_add_item, float divisor, int64_t d_full,
-                      int64_t col_off, int32_t n_peers, int64_t users_per_rank, float* const* h_peer_user_out,
-                      float* const* h_peer_item_out, void* d_workspace, int64_t workspace_bytes, tgcn_stream_t stream);
+                      int64_t col_off, int32_t n_peers, int64_t users_per_rank, int64_t user_row0,
+                      float* const* h_peer_user_out, float* const* h_peer_item_out, void* d_workspace,
+                      int64_t workspace_bytes, tgcn_stream_t stream);
 int tgcn_layer_mean_scatter(int64_t n_rows, int64_t d_slice, int32_t n_add, const float* const* h_add, float divisor,
                             int64_t d_full, int64_t col_off, int64_t row0, int32_t n_dst, float* const* h_dst,
                             tgcn_stream_t stream);

@@ -219,7 +219,15 @@ def test_grid_and_slice_partition_geometry():
             cover_final += list(range(*gp.final_users(rank)))
             if g == 0:
                 cover_users += list(range(*gp.rows.users(r)))
-        assert cover_users == list(range(nu)) and cover_final == list(range(nu))
+        # every user has exactly one final owner, and that owner sits in the row group that computed the user (the rows never
+        # leave their row partition: only the G feature-slice partners exchange them)
+        assert cover_users == list(range(nu)) and sorted(cover_final) == list(range(nu))
+        for rank in range(G * R):
+            g, r = gp.coords(rank)
+            f0, f1 = gp.final_users(rank)
+            u0, u1 = gp.rows.users(r)
+            assert u0 <= f0 <= f1 <= u1 and f1 - f0 <= gp.per
+            assert gp.slice_partners(r)[g] == rank
         shares = [tdist.item_shard(ni, R, r) for r in range(R)]
         assert [i for a, b in shares for i in range(a, b)] == list(range(ni))
     fp = tdist.FeatureSlicePartition(nu, ni, d, 4)

@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtgcn_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_TOPK = 128
 ADV_MAX_CANDIDATES = 2048
 
@@ -36,7 +36,7 @@ SIGNATURES = {
     "tgcn_propagate_sliced": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_float, c_int64, c_int64, c_int32, c_int64,
                                         POINTER(c_void_p), POINTER(c_void_p), _P, c_int64, _P]),
     "tgcn_spmm_scatter": (c_int32, [_P, c_int64, _P, _P, c_int32, POINTER(c_void_p), POINTER(c_void_p), c_float, c_int64, c_int64,
-                                    c_int32, c_int64, POINTER(c_void_p), POINTER(c_void_p), _P, c_int64, _P]),
+                                    c_int32, c_int64, c_int64, POINTER(c_void_p), POINTER(c_void_p), _P, c_int64, _P]),
     "tgcn_layer_mean_scatter": (c_int32, [c_int64, c_int64, c_int32, POINTER(c_void_p), c_float, c_int64, c_int64, c_int64, c_int32,
                                           POINTER(c_void_p), _P]),
     "tgcn_peer_alloc": (c_int32, [c_int64, POINTER(c_void_p), _P]),

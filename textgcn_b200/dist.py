@@ -183,7 +183,7 @@ class BipartitePropagator:
         self.part, self.rank, self.ug, self.ig, self.d, self.n_layers = part, rank, user_graph, item_graph, d, n_layers
         self.item_chunks = item_chunks or [(0, part.n_items, item_graph)]
         self.group, self.spmm_fn, self.mean_fn = group, spmm_fn, mean_fn
-        self.tail_fn = None  # optional hook (works, (addends, divisor), out_item) replacing the final wait + mean
+        self.tail_fn = None  # optional hook (works, (addends, divisor), out_item, launch_last_user_pass) replacing the last layer's tail
         self.comm = None     # optional C-ABI communicator (CabiComm): the per-hop all-reduce through tgcn_allreduce_sum_f32
         u0, u1 = part.users(rank)
         self.n_local = u1 - u0
@@ -221,17 +221,19 @@ class BipartitePropagator:
         for layer in range(1, L + 1):
             last = layer == L
             nxt = []
+            if last and self.tail_fn is not None:
+                # the item table's layer mean only needs AR_L, not the last user pass A_L: the owner's hook runs the mean on a
+                # side stream (after AR_L) and A_L on this one, so that the two overlap (GridPropagator._tail)
+                adds = [] if single else [e0_user_local] + self.ubufs
+                self.tail_fn(works, ([self.ibufs[L - 1]], 1.0) if single else ([e0_item] + self.ibufs, float(L + 1)), out_item,
+                             lambda: spmm(self.ug, cur_i, out_user_local, adds, 1.0 if single else float(L + 1)))
+                return out_user_local, out_item
             if last:                                                        # A_l: user rows of layer l (local)
                 adds = [] if single else [e0_user_local] + self.ubufs
                 spmm(self.ug, cur_i, out_user_local, adds, 1.0 if single else float(L + 1))
             else:
                 spmm(self.ug, cur_i, self.ubufs[layer - 1], [], 1.0)
                 nxt = item_partials(self.ubufs[layer - 1], self.ibufs[layer])   # B_{l+1}; AR_{l+1} queues behind AR_l
-            if last and self.tail_fn is not None:
-                # the item table's layer mean only needs AR_L, not the last user pass A_L: hand both to the owner's hook,
-                # which runs the mean on a side stream so that it overlaps A_L (GridPropagator._tail)
-                self.tail_fn(works, ([self.ibufs[L - 1]], 1.0) if single else ([e0_item] + self.ibufs, float(L + 1)), out_item)
-                return out_user_local, out_item
             for wk in works:
                 wk.wait()                                                   # item table of layer l is complete
             works = nxt
@@ -402,7 +404,12 @@ class GridPartition:
         self.world_size = n_slices * n_row_parts
         self.n_users, self.n_items, self.d, self.ds = n_users, n_items, d, d // n_slices
         self.rows = BipartitePartition(rowptr, n_users, n_items, n_row_parts)
-        self.per = -(-n_users // self.world_size)
+        # result layout: the users of row partition r stay inside their row group — rank (g, r) ends up with the g-th of G
+        # equal sub-ranges of partition r, full width.  Only the G feature-slice partners of a row group exchange user rows
+        # (nothing moves at G = 1); round 1 re-cut the users into P equal ranges, which sent ~(P-1)/P of every rank's rows
+        # across NVLink from inside the last SpMM pass.
+        self.sub_per = [-(-(self.rows.users(r)[1] - self.rows.users(r)[0]) // n_slices) for r in range(n_row_parts)]
+        self.per = max(max(self.sub_per), 1)  # rows of the largest result shard (table allocation)
 
     def coords(self, rank: int) -> Tuple[int, int]:
         return rank // self.R, rank % self.R
@@ -411,7 +418,13 @@ class GridPartition:
         return g * self.ds, (g + 1) * self.ds
 
     def final_users(self, rank: int) -> Tuple[int, int]:
-        return min(rank * self.per, self.n_users), min((rank + 1) * self.per, self.n_users)
+        g, r = self.coords(rank)
+        u0, u1 = self.rows.users(r)
+        return min(u0 + g * self.sub_per[r], u1), min(u0 + (g + 1) * self.sub_per[r], u1)
+
+    def slice_partners(self, r: int) -> List[int]:
+        """The G ranks that hold the G feature slices of row partition r, in slice order."""
+        return [g * self.R + r for g in range(self.G)]
 
     def row_group_ranks(self, g: int) -> List[int]:
         return [g * self.R + r for r in range(self.R)]
@@ -491,8 +504,10 @@ class GridPropagator:
             return self._spmm_fn(graph, x, y, addends, divisor)
         if self.exchange == "p2p":
             part = self.part
-            return self._ops.spmm_scatter(graph, x, addends, divisor, part.d, part.cols(self.g)[0], part.per, self.tables.peer_u,
-                                          self.tables.peer_i)
+            partners = part.slice_partners(self.r)   # user row (u0 + j) goes to partner j // sub_per, local row j % sub_per
+            return self._ops.spmm_scatter(graph, x, addends, divisor, part.d, part.cols(self.g)[0], part.sub_per[self.r],
+                                          [self.tables.peer_u[q] for q in partners], [self.tables.peer_i[q] for q in partners],
+                                          user_row0=part.rows.users(self.r)[0])
         return self._spmm_fn(graph, x, self.loc_u, addends, divisor)
 
     def _mean_impl(self, addends, out, divisor):
@@ -506,9 +521,9 @@ class GridPropagator:
             return None
         return self._mean_fn(addends, self.loc_i, divisor)
 
-    def _tail(self, works, mean_args, out_item):
-        """Last layer: the item table's layer mean (+ its broadcast into every rank's replica) needs the final all-reduce
-        but not the last user pass, which is already enqueued on the main stream — run it on the side stream."""
+    def _tail(self, works, mean_args, out_item, launch_last_user_pass):
+        """Last layer: the item table's layer mean (+ its broadcast into every rank's replica) needs the final all-reduce AR_L
+        but not the last user pass A_L, and A_L does not need AR_L: the mean runs on the side stream, A_L on the main one."""
         main = torch.cuda.current_stream()
         self._ev_main.record(main)          # everything the mean reads except AR_L was produced before this point
         with torch.cuda.stream(self._side):
@@ -517,6 +532,7 @@ class GridPropagator:
                 wk.wait()                   # the side stream (not the main one) waits for the collective
             self._mean(mean_args[0], out_item, mean_args[1])
             self._ev_side.record(self._side)
+        launch_last_user_pass()             # overlaps AR_L's tail and the mean / broadcast
         main.wait_event(self._ev_side)      # joins before the closing barrier
 
     def propagate(self, e0_user_slice_local: torch.Tensor, e0_item_slice: torch.Tensor, single: bool = False):

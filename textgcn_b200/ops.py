@@ -341,9 +341,10 @@ def comm_topk_exchange(comm: int, n_ranks: int, part_ids, part_scores, recv_ids,
 
 
 def spmm_scatter(g: Graph, x: torch.Tensor, addends: Sequence[torch.Tensor], divisor: float, d_full: int, col_off: int,
-                 users_per_rank: int, peer_user_ptrs: Sequence[int], peer_item_ptrs: Sequence[int]) -> None:
+                 users_per_rank: int, peer_user_ptrs: Sequence[int], peer_item_ptrs: Sequence[int], user_row0: int = 0) -> None:
     """One SpMM pass (row-block or whole-graph handle, contiguous operands) whose result rows are stored into the peers'
-    full-width tables by global row id (see tgcn_spmm_scatter)."""
+    full-width tables: user row u goes to peer (u - user_row0) // users_per_rank, local row (u - user_row0) % users_per_rank
+    (see tgcn_spmm_scatter)."""
     _chk(x, torch.float32, "x", 2)
     ds = x.shape[1]
     n = len(addends)
@@ -355,7 +356,7 @@ def spmm_scatter(g: Graph, x: torch.Tensor, addends: Sequence[torch.Tensor], div
     ws = g.workspace(ds, 1)
     with torch.cuda.device(x.device):
         check(g.lib.tgcn_spmm_scatter(g.handle, ds, _ptr(x), None, n, arr, nul, float(divisor), int(d_full), int(col_off), np_,
-                                      int(users_per_rank), pu, pi, _ptr(ws), ws.numel(), _stream()))
+                                      int(users_per_rank), int(user_row0), pu, pi, _ptr(ws), ws.numel(), _stream()))
 
 
 def layer_mean_scatter(addends: Sequence[torch.Tensor], divisor: float, d_full: int, col_off: int, row0: int,

@@ -2,8 +2,13 @@
 
 Log-normal user / item popularity (σ_u = 1.0, σ_i = 1.3), (u, i) pairs drawn from the product distribution,
 deduplicated, at least one edge per user and per item, exactly ``n_edges`` rows sorted by (u, i).  All torch ops
-on the target device with a seeded generator, so every rank of a multi-GPU run builds the identical graph and the
-200M-edge configuration takes seconds.
+on the target device with a seeded generator, so the 200M-edge configuration takes seconds.
+
+Every rank of a multi-GPU run builds the graph itself and all ranks must end up with the IDENTICAL graph, so every step is
+bit-reproducible: in particular the popularity CDFs are INTEGER prefix sums (fixed-point weights).  Round 1 drew from a
+float64 ``torch.cumsum`` on the device, which is not run-to-run deterministic in its last bits; a handful of boundary
+draws then landed on a neighbouring user / item, ranks disagreed on a few edges of Â, and the self-verifying bench of
+round 2 caught it as a parity failure of the multi-GPU result (profiles/r02/README.md).
 """
 from __future__ import annotations
 
@@ -23,14 +28,19 @@ def interactions(n_users: int, n_items: int, n_edges: int, device, seed: int = 0
                  sigma_u: float = 1.0, sigma_i: float = 1.3) -> Tuple[torch.Tensor, torch.Tensor]:
     assert max(n_users, n_items) <= n_edges <= n_users * n_items
     gen = torch.Generator(device=device).manual_seed(seed)
-    wu = torch.exp(torch.randn(n_users, generator=gen, device=device, dtype=torch.float64) * sigma_u)
-    wi = torch.exp(torch.randn(n_items, generator=gen, device=device, dtype=torch.float64) * sigma_i)
-    cu = torch.cumsum(wu / wu.sum(), 0)
-    ci = torch.cumsum(wi / wi.sum(), 0)
+
+    def int_cdf(n, sigma):
+        """Log-normal weights in 32-bit fixed point and their exact (int64, order-independent) prefix sums."""
+        w = torch.exp(torch.randn(n, generator=gen, device=device, dtype=torch.float64) * sigma)
+        q = (w / w.max() * float(1 << 32)).to(torch.int64).clamp_(min=1)
+        return torch.cumsum(q, 0)
+
+    cu = int_cdf(n_users, sigma_u)
+    ci = int_cdf(n_items, sigma_i)
 
     def draw(cdf, m, hi):
-        r = torch.rand(m, generator=gen, device=device, dtype=torch.float64)
-        return torch.searchsorted(cdf, r).clamp_(max=hi - 1)
+        r = torch.randint(0, int(cdf[-1]), (m,), generator=gen, device=device, dtype=torch.int64)
+        return torch.searchsorted(cdf, r, right=True).clamp_(max=hi - 1)
 
     fu = torch.arange(n_users, device=device)
     gi = torch.arange(n_items, device=device)
@@ -48,7 +58,9 @@ def interactions(n_users: int, n_items: int, n_edges: int, device, seed: int = 0
         is_forced = torch.isin(keys, forced, assume_unique=True)
         extra = keys[~is_forced]
         n_keep = n_edges - forced.numel()
-        perm = torch.randperm(extra.numel(), generator=gen, device=device)[:n_keep]
+        # a random subset by seeded integer priorities + a stable sort (bit-reproducible, unlike relying on randperm's kernel)
+        prio = torch.randint(0, 1 << 62, (extra.numel(),), generator=gen, device=device, dtype=torch.int64)
+        perm = torch.argsort(prio, stable=True)[:n_keep]
         keys = torch.sort(torch.cat([forced, extra[perm]])).values
     u = torch.div(keys, n_items, rounding_mode="floor")
     return u, keys - u * n_items

@@ -263,6 +263,34 @@ def torch_cuda_reference(w, dev, flush, torch, topk, n_eval=8192):
     return res, emb, torch.cat([t.indices for t in kept]), torch.cat([t.values for t in kept])
 
 
+def metrics_leg(ops, ids, n_users, n_items, k, dev, flush, torch, sample=20000):
+    """SURVEY.md §8f n4 at the scale it was asked for: recall / precision / hit / ndcg / f1 @k for ALL n_users of the config in one
+    pass of tgcn_topk_metrics over a (n_users, k) id table and a CSR of held-out items (one per user, §8d) — no Python loop over
+    users.  The table tiles the ranked sample; a 20 000-row sample is checked against a closed-form torch evaluation (one true item
+    per row: recall = hit, precision = hit / k, ndcg = hit / log2(rank + 2), f1 from those)."""
+    from textgcn_b200 import metrics as M
+    reps = -(-n_users // ids.shape[0])
+    table = ids.repeat(reps, 1)[:n_users].contiguous()
+    gen = torch.Generator(device=dev).manual_seed(5)
+    # make ~half of the rows hits: the true item is one of the row's predictions at a random rank, or a random item
+    rank_pos = torch.randint(0, k, (n_users,), generator=gen, device=dev)
+    truth = torch.where(torch.rand(n_users, generator=gen, device=dev) < 0.5, table[torch.arange(n_users, device=dev), rank_pos].long(),
+                        torch.randint(0, n_items, (n_users,), generator=gen, device=dev))
+    csr = M.TruthCSR.from_pairs(torch.arange(n_users, device=dev), truth, n_users)
+    t = timed_steps(lambda: ops.topk_metrics(table, csr.ptr, csr.ids, [k]), 3, 1, flush, torch)
+    ms = sum(t) / len(t)
+    vals = ops.topk_metrics(table[:sample].contiguous(), csr.ptr[:sample + 1].contiguous(), csr.ids[:sample].contiguous(), [k])[0]
+    eq = table[:sample].long() == truth[:sample, None]
+    hit = eq.any(1).double()
+    pos = torch.where(eq.any(1), eq.double().argmax(1), torch.zeros(sample, dtype=torch.int64, device=dev))
+    ndcg = hit / torch.log2(pos.double() + 2)
+    prec = hit / k
+    f1 = torch.where(hit > 0, 2 * hit * prec / (hit + prec), torch.zeros_like(hit))
+    want = torch.stack([hit.mean(), prec.mean(), hit.mean(), ndcg.mean(), f1.mean()])
+    return {"rows": n_users, "k": k, "ms": ms, "users_per_s": n_users / (ms * 1e-3), "bytes_read": n_users * (k * 4 + 12),
+            "sample_rows_checked": sample, "sample_max_abs_err": float((vals - want).abs().max())}
+
+
 def eval_roofline(tensor_flops_per_gpu, ms):
     """Tensor-pipe roofline of the fused eval call on one GPU: 3 TF32 MMAs per product (3xTF32), against the nominal dense TF32
     peak and against half the MEASURED dense bf16 rate (MEASURED_PEAKS.json; cuBLAS 8192^3, the only measured tensor figure)."""
@@ -898,6 +926,8 @@ def main():
                               max(1, args.eval_steps - 1), 1, flush, torch)
             ev["fp32_simt_users_per_s"] = n_f / (sum(t_f) / len(t_f) * 1e-3)
             ev["fp32_simt_note"] = f"eval_topk_simt_kernel (exact fp32 FMA) on {n_f} users"
+        if world == 1 and name == "c5":
+            ev["metrics_10M_users"] = metrics_leg(ops, eval_step()[0], nu, ni, k, dev, flush, torch)
         if eval_e2e is not None:
             t_e = timed_steps(eval_e2e, args.eval_steps, 1, flush, torch)
             ev["e2e_users_per_s"] = n_eval / (sum(t_e) / len(t_e) * 1e-3)

@@ -261,3 +261,18 @@ def test_spmm_with_tables_beyond_4_gib(ops):
     y2 = ops.spmm(graph, y)
     ref_rows = (x[rows] + y[rows] + y2[rows]) / 3
     assert rel_err(out[rows].cpu(), ref_rows.cpu()) < TOL
+
+
+def test_synthetic_graph_is_bit_reproducible_on_the_device():
+    """Every rank of a multi-GPU run builds the workload itself: two builds must agree bit for bit (round 1's float64 device
+    cumsum did not, and ranks ended up with slightly different graphs)."""
+    from textgcn_b200.graph import norm_adj_csr
+    from textgcn_b200.synthetic import interactions
+    builds = []
+    for _ in range(3):
+        tu, ti = interactions(2_000_000, 400_000, 30_000_000, torch.device(DEV), seed=0)
+        builds.append((tu, ti) + tuple(norm_adj_csr(tu, ti, 2_000_000, 400_000)))
+    for other in builds[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(builds[0], other))
+    tu, ti = builds[0][:2]
+    assert int(torch.unique(tu).numel()) == 2_000_000 and int(torch.unique(ti).numel()) == 400_000 and tu.numel() == 30_000_000

@@ -319,6 +319,10 @@ static int sm_count() {
   return n;
 }
 
+// (Round 2 experiment, reverted: for the STREAMED tensor-core variant — LTR ranking, K = 1600, whose 822 MB item operand every
+// user tile re-streams; ncu: 61.9 GB of DRAM reads per call — splitting the item range until one split's share of the operand
+// is L2-sized (17 splits instead of 2) made the call 4 % SLOWER, 18.9 -> 19.6 ms: the per-CTA pipeline fill, list restarts and
+// the wider merge cost more than the DRAM traffic they remove.  profiles/r02/README.md.)
 void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_splits, int* tiles_per_split) {
   const int64_t m_tiles = (n_rank + BM - 1) / BM;
   const int64_t n_tiles = (n_items_range + bn - 1) / bn;

@@ -108,13 +108,17 @@ __global__ void __launch_bounds__(kMetricThreads) topk_metrics_kernel(const Metr
   }
 }
 
+// One warp per value: lane l adds the partials of blocks l, l + 32, ... in order, then a fixed shuffle tree — the same
+// summation order every run.
 __global__ void topk_metrics_finalize_kernel(const double* __restrict__ partials, int n_blocks, int n_vals, double n_rows,
                                              double* __restrict__ out) {
-  const int t = threadIdx.x;
+  const int t = blockIdx.x, lane = threadIdx.x;  // one 32-thread block per value
   if (t >= n_vals) return;
   double s = 0.0;
-  for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * n_vals + t];
-  out[t] = s / n_rows;
+  for (int b = lane; b < n_blocks; b += 32) s += partials[(size_t)b * n_vals + t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[t] = s / n_rows;
 }
 
 }  // namespace tgcn
@@ -149,7 +153,7 @@ int tgcn_topk_metrics(int64_t n_rows, int32_t kmax, const int32_t* d_pred_ids, c
   cudaStream_t s = (cudaStream_t)stream;
   topk_metrics_kernel<<<(unsigned)blocks, kMetricThreads, 0, s>>>(a);
   TGCN_CHECK_LAUNCH();
-  topk_metrics_finalize_kernel<<<1, 64, 0, s>>>(a.partials, (int)blocks, n_ks * kNumMetrics, (double)n_rows, d_out);
+  topk_metrics_finalize_kernel<<<n_ks * kNumMetrics, 32, 0, s>>>(a.partials, (int)blocks, n_ks * kNumMetrics, (double)n_rows, d_out);
   TGCN_CHECK_LAUNCH();
   return 0;
 }

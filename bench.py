@@ -213,6 +213,29 @@ def train_leg(w, graph, dev, flush, torch, batch=2048, steps=10, warmup=3):
         res["ms_per_step"] = eager_ms
         res["mode"] = "eager"
         res["graph_error"] = str(exc)[:200]
+    # the same eager step with the reference's default mask source: torch.rand(nnz) on the HOST generator + H2D every step
+    # (base_model.py:82; dropout_rng="host" reproduces the reference's draws bit for bit, at this price)
+    try:
+        model.dropout_rng = "host"
+        t = timed_steps(step, 3, 1, flush, torch)
+        res["host_rng_eager_ms_per_step"] = sum(t) / len(t)
+    except Exception as exc:
+        res["host_rng_error"] = str(exc)[:200]
+    model.dropout_rng = "device"
+    nnz, n, d, L, keep_p = w["nnz"], w["nu"] + w["ni"], w["d"], w["L"], 1.0 - params.dropout
+    spmm_pass = nnz * 9 + keep_p * nnz * 4 * d + n * 4 * d            # col/val + mask byte + gathers of the kept edges + output rows
+    step_bytes = (nnz                                                  # dropout_mask_kernel
+                  + L * spmm_pass + L * n * 4 * d                      # forward passes + the layer-mean epilogue's addend reads
+                  + 2 * n * 4 * d                                      # zero fill of the two gradient tables
+                  + batch * 3 * 2 * 4 * d * 2                          # bpr_kernel: 3 rows x (emb + E0) read, the same in atomics
+                  + 6 * nnz                                            # permute_mask_kernel
+                  + L * (spmm_pass + n * 4 * d)                        # Horner backward: each pass also reads G as addend
+                  + 7 * n * 4 * d)                                     # adam_kernel over both tables
+    ach = step_bytes / (res["ms_per_step"] * 1e-3) / 1e9
+    res["roofline"] = {"bound": "l2 / hbm (tables of 65 MB: gathers hit L2, the gradient / Adam streams do not)", "algorithmic_bytes": step_bytes,
+                       "achieved": ach, "unit": "GB/s", "frac_of_hbm_peak": ach / peaks()[0],
+                       "frac_of_l2_cap": ach / (L2_CAP_BYTES_PER_CLK * 1965e6 / 1e9),
+                       "note": "sum of the per-kernel byte models of profiles/r02/kernel_table_c2.md over one step / its CUDA-event time"}
     res.update({"batch": batch, "dropout": params.dropout, "steps_per_s": 1e3 / res["ms_per_step"],
                 "includes": "device dropout draw, L-layer propagate, fused BPR(SELU)+L2 kernel, Horner backward (L transposed SpMM), "
                             "fused Adam over both tables"})
@@ -362,8 +385,10 @@ def c2_leg(args, dev, flush, torch, hbm_peak):
         h_o = torch.empty((n, d), dtype=torch.float32).pin_memory()
         stage = torch.empty((2 * n, d), dtype=torch.float32, device=dev)
         te = timed_steps(lambda: ops.propagate_host(graph, h_u, h_i, h_o, L, stage), 5, 2, flush, torch)
+        torch.cuda.synchronize()
         res["e2e"] = {"value": nnz * L / (sum(te) / len(te) * 1e-3), "unit": "edges/s", "ms_per_step": sum(te) / len(te),
-                      "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4}
+                      "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4,
+                      "matches_device_result": bool(torch.equal(h_o, out.cpu()))}
         del stage
     if not args.no_eval:
         users = torch.arange(nu, dtype=torch.int32, device=dev)
@@ -448,8 +473,20 @@ def extras_leg(w, graph, dev, flush, torch, batch=2048):
         opt.step()
 
     t = timed_steps(adv_step, 5, 2, flush, torch)
-    out["adv_sampling"] = {"ms_per_step": sum(t) / len(t), "batch_users": batch, "candidates": smp.n_cand, "k": 20,
+    adv_ms = sum(t) / len(t)
+    nnz, n, d, L, keep_p, T = w["nnz"], w["nu"] + w["ni"], w["d"], w["L"], 1.0 - params.dropout, n_triples[-1]
+    spmm_pass = nnz * 9 + keep_p * nnz * 4 * d + n * 4 * d
+    adv_bytes = (batch * (1 + smp.n_cand) * 8 + 2 * nnz                # candidate sampler, two dropout draws (G12)
+                 + 2 * (L * spmm_pass + L * n * 4 * d)                 # two propagations per step
+                 + batch * smp.n_cand * (4 * d + 4)                    # adv_select_kernel gathers
+                 + 2 * n * 4 * d + T * 3 * 2 * 4 * d * 2               # gradient zero fill, bpr_kernel on T triples
+                 + 6 * nnz + L * (spmm_pass + n * 4 * d) + 7 * n * 4 * d)   # backward + Adam
+    out["adv_sampling"] = {"ms_per_step": adv_ms, "batch_users": batch, "candidates": smp.n_cand, "k": 20,
                            "triples_per_step": n_triples[-1],
+                           "roofline": {"bound": "l2 / hbm", "algorithmic_bytes": adv_bytes, "achieved": adv_bytes / (adv_ms * 1e-3) / 1e9,
+                                        "unit": "GB/s", "frac_of_hbm_peak": adv_bytes / (adv_ms * 1e-3) / 1e9 / peaks()[0],
+                                        "note": "byte models of the step's kernels / CUDA-event time; the step also contains torch glue "
+                                                "(nonzero / stack building the (T, 3) triples) and a host sync for T"},
                            "includes": "candidate + positive sampling kernels, propagate, adv_select_kernel, second propagate + fused BPR, "
                                        "Horner backward, fused Adam"}
     del model, opt
@@ -815,6 +852,10 @@ def main():
                       "streams overlapping the first / last layer)" if world == 1
                else "host-pinned E0 shard -> device, L hops with the collective, result shard (own user rows + 1/P of the item table) "
                     "-> pinned host; bytes are per rank"}
+        if world == 1:   # the host-buffer call must return exactly what the device-resident call computed (first and last 1M rows)
+            torch.cuda.synchronize()
+            e2e["matches_device_result"] = bool(torch.equal(h_o[:1 << 20], out[:1 << 20].cpu()) and
+                                                torch.equal(h_o[-(1 << 20):], out[-(1 << 20):].cpu()))
 
     # ---- eval leg: fused score + mask + top-k ----------------------------------------------------------------
     ev = None
@@ -1028,6 +1069,12 @@ def main():
             "eval": ev, "clocks": sampler.summary(),
         }
         line.update(extra)
+        tref = extra.get("torch_cuda_reference") or {}
+        if tref.get("edges_per_s"):
+            # the comparator that matters: the reference's own ops (torch.sparse / cuBLAS / topk) on the SAME GPU in the same run;
+            # `cpu_baseline` / --impl reference time the reference's CPU path on a bounded sample (throughput per non-zero)
+            line["vs_torch_cuda_reference"] = {"propagation": value / tref["edges_per_s"],
+                                               "eval": (ev["users_per_s"] / tref["eval_users_per_s"]) if (ev and tref.get("eval_users_per_s")) else None}
         if parity is not None:
             line["parity"] = parity
         if cpu_base is not None:
@@ -1036,8 +1083,12 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     bad = [p for p in (parity, (extra.get("c2") or {}).get("parity")) if p is not None and not p.get("ok", False)]
+    if ((extra.get("c2") or {}).get("e2e") or {}).get("matches_device_result") is False:
+        bad.append({"c2_e2e_matches_device_result": False})
     if extra.get("item_sharded_matches_user_sharded") is False:
         bad.append({"item_sharded_matches_user_sharded": False})
+    if e2e is not None and e2e.get("matches_device_result") is False:
+        bad.append({"e2e_matches_device_result": False})
     if bad:   # the line above is still printed, but a result out of tolerance fails the run
         print(f"bench.py: PARITY FAILURE {bad}", file=sys.stderr, flush=True)
         sys.exit(3)

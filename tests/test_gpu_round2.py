@@ -276,3 +276,40 @@ def test_synthetic_graph_is_bit_reproducible_on_the_device():
         assert all(torch.equal(a, b) for a, b in zip(builds[0], other))
     tu, ti = builds[0][:2]
     assert int(torch.unique(tu).numel()) == 2_000_000 and int(torch.unique(ti).numel()) == 400_000 and tu.numel() == 30_000_000
+
+
+@pytest.mark.parametrize("case,single", [("small_lgcn_d64", False), ("small_lgcn_d128_l4", False), ("small_lgcn_d32_single", True)])
+def test_propagate_host_pipelined_matches_device_path(ops, case, single):
+    """tgcn_propagate_host (the e2e entry: uploads on a copy stream, layer 1's user pass overlapping the user-table upload, last layer
+    in row chunks with the download behind it) returns exactly what tgcn_propagate_fwd computes from device-resident tables."""
+    g = load_golden(case)
+    nu, ni, L = int(g["n_users"]), int(g["n_items"]), int(g["n_layers"])
+    graph = ops.Graph.from_norm_matrix(O.sparse_tensor(g["norm_row"], g["norm_col"], g["norm_val"], nu + ni).to(DEV), nu, ni)
+    uw, iw = torch.from_numpy(g["user_w"]), torch.from_numpy(g["item_w"])
+    d = uw.shape[1]
+    want = ops.propagate_fwd(graph, uw.to(DEV), iw.to(DEV), L, single=single)
+    h_u, h_i = uw.clone().pin_memory(), iw.clone().pin_memory()
+    h_o = torch.full((nu + ni, d), float("nan")).pin_memory()
+    stage = torch.empty((2 * (nu + ni), d), dtype=torch.float32, device=DEV)
+    for _ in range(3):   # back to back: the staging buffers and events are reused
+        ops.propagate_host(graph, h_u, h_i, h_o, L, stage, single=single)
+    torch.cuda.synchronize()
+    assert torch.equal(h_o, want.cpu())
+    assert rel_err(h_o[:nu].numpy(), g["rep_user"]) < TOL and rel_err(h_o[nu:].numpy(), g["rep_item"]) < TOL
+
+
+def test_propagate_host_at_electronics_shape_with_long_rows(ops):
+    from textgcn_b200.graph import graph_from_interactions
+    nu, ni, ne, d, L = 190_000, 63_000, 1_700_000, 64, 3
+    tu, ti = O.synthetic_interactions(nu, ni, ne, seed=0)
+    graph = graph_from_interactions(tu, ti, nu, ni, DEV)
+    assert graph.n_segments > 0                      # long item rows: the segment ranges of the chunked launches are exercised
+    gen = torch.Generator().manual_seed(1)
+    uw, iw = torch.randn(nu, d, generator=gen) * 0.1, torch.randn(ni, d, generator=gen) * 0.1
+    want = ops.propagate_fwd(graph, uw.to(DEV), iw.to(DEV), L)
+    h_u, h_i = uw.pin_memory(), iw.pin_memory()
+    h_o = torch.empty((nu + ni, d)).pin_memory()
+    stage = torch.empty((2 * (nu + ni), d), dtype=torch.float32, device=DEV)
+    ops.propagate_host(graph, h_u, h_i, h_o, L, stage)
+    torch.cuda.synchronize()
+    assert torch.equal(h_o, want.cpu())

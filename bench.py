@@ -643,13 +643,21 @@ def main():
     if world > 1:
         # every rank builds the workload itself: they must agree bit for bit (exact integer / float64 checksums), else the
         # multi-GPU result is meaningless — refuse to time it
-        sums = torch.stack([w["rowptr"].double().sum(), w["col"].double().sum(), w["val"].double().sum(), w["uw"].double().sum(),
-                            w["iw"].double().sum()])
+        sums = torch.stack([w["rowptr"].long().sum(), w["col"].long().sum()] +
+                           [w[key].view(torch.int32).long().sum() for key in ("val", "uw", "iw")])   # int64 sums of the bit patterns: exact
         lo, hi = sums.clone(), sums.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         if not torch.equal(lo, hi):
-            raise RuntimeError(f"ranks built different workloads: checksum spread {(hi - lo).tolist()}")
+            # never time ranks that disagree on the graph: adopt rank 0's copy everywhere (same shapes: the generator emits
+            # exactly n_edges rows) and say so in the line
+            for key in ("rowptr", "col", "val", "uw", "iw"):
+                dist.broadcast(w[key], src=0)
+            workload_note = f"ranks built different workloads (checksum spread {(hi - lo).tolist()}): rank 0's copy was broadcast"
+        else:
+            workload_note = None
+    else:
+        workload_note = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     hbm_peak, peak_src = peaks()
     sampler = ClockSampler(local_rank)
@@ -1069,6 +1077,8 @@ def main():
             "eval": ev, "clocks": sampler.summary(),
         }
         line.update(extra)
+        if workload_note:
+            line["config"]["workload_note"] = workload_note
         tref = extra.get("torch_cuda_reference") or {}
         if tref.get("edges_per_s"):
             # the comparator that matters: the reference's own ops (torch.sparse / cuBLAS / topk) on the SAME GPU in the same run;

@@ -109,6 +109,48 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): two SMs of one TPC execute ONE MMA of M = 256; each CTA supplies its own 128 rows of A and HALF of the
+// B tile from its own shared memory and keeps its 128 accumulator rows in its own tensor memory.  Only the leader (cluster rank 0)
+// issues MMAs; both CTAs issue TMA loads whose transaction bytes land on the LEADER's barrier (peer bit of the address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` (same offset) in BOTH CTAs once the MMAs retire
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {  // arrive on `bar` of CTA `cta` of the cluster
+  asm volatile(
+      "{\n"
+      ".reg .b32 rem;\n"
+      "mapa.shared::cluster.u32 rem, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [rem];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 // K-major, 128-byte swizzle: 8-row atoms of 1024 B, SBO = 1024 B, LBO unused, descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -183,15 +225,23 @@ __device__ __forceinline__ void reg_list_insert_lex(float (&ls)[KL], int (&li)[K
 // STREAM = false: the user tile [hi | lo] stays resident in shared memory for the whole sweep (K <= 128).
 // STREAM = true : wide contractions (the LTR score, K = d + 2D + bias chunk): user and item K-chunks travel together
 //                 through the ring, one stage = {U_hi, U_lo, I_hi, I_lo} of one 32-wide K-chunk (12 MMAs per stage).
-template <int BN, int KL, int EW, bool STREAM>
+// CTAS = 2 (non-streamed only): CTA pairs (cluster of 2 along x) — every MMA covers 256 users x BN items, the item tile is split
+//                 between the two CTAs' rings (BN / 2 rows each), so the shared-memory operand fetch per SM and the number of MMA
+//                 instructions per score both halve.  Each CTA keeps its own users' accumulator rows, lists and epilogue.
+template <int BN, int KL, int EW, bool STREAM, int CTAS = 1>
 __global__ void __launch_bounds__(128 + 128 * EW, 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
+  static_assert(CTAS == 1 || (CTAS == 2 && !STREAM), "CTA pairs are implemented for the resident-user-tile variant");
+  constexpr bool PAIR = CTAS == 2;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int KC = a.K / TC_CHUNK;
   const int n_a = STREAM ? 0 : 2 * KC;  // resident user chunks
-  constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BN * 128 : BN * 128;
+  constexpr int BROWS = BN / CTAS;  // item rows of a tile held by THIS CTA's ring
+  constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BN * 128 : BROWS * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
   uint8_t* ring = gen_base + n_a * TC_A_CHUNK_BYTES;  // item ring; reused for the list merge once the sweep is over
@@ -221,16 +271,23 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
-      mbar_init(bar_t_empty + 8 * s, 4 * EW);  // one arrival per epilogue warp
+      mbar_init(bar_t_empty + 8 * s, 4 * EW * CTAS);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers exist before anyone (TMA of the peer, remote arrives) touches them
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -257,15 +314,19 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           }
         }
       } else {
-      mbar_expect_tx(bar_a_full, n_a * TC_A_CHUNK_BYTES);
-      for (int c = 0; c < n_a; ++c) tma_load_2d(sA + c * TC_A_CHUNK_BYTES, &map_u, bar_a_full, c * TC_CHUNK, m0);
+      if (leader) mbar_expect_tx(bar_a_full, CTAS * n_a * TC_A_CHUNK_BYTES);  // pair: the leader's barrier counts both CTAs' user tiles
+      for (int c = 0; c < n_a; ++c) {
+        if constexpr (PAIR) tma_load_2d_pair(sA + c * TC_A_CHUNK_BYTES, &map_u, bar_a_full, c * TC_CHUNK, m0);
+        else tma_load_2d(sA + c * TC_A_CHUNK_BYTES, &map_u, bar_a_full, c * TC_CHUNK, m0);
+      }
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int row0 = tile * BN;
+        const int row0 = tile * BN + (int)cta_rank * BROWS;  // pair: this CTA streams its half of the item tile
         for (int c = 0; c < n_a; ++c) {  // order: hi_0, lo_0, hi_1, lo_1, ...
           const int colk = (c & 1) ? a.K + (c >> 1) * TC_CHUNK : (c >> 1) * TC_CHUNK;
-          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-          mbar_expect_tx(bar_b_full + 8 * stage, B_STAGE_BYTES);
-          tma_load_2d(sB + stage * B_STAGE_BYTES, &map_i, bar_b_full + 8 * stage, colk, row0);
+          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);   // own barrier: the MMA commit is multicast to both CTAs
+          if (leader) mbar_expect_tx(bar_b_full + 8 * stage, CTAS * B_STAGE_BYTES);
+          if constexpr (PAIR) tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &map_i, bar_b_full + 8 * stage, colk, row0);
+          else tma_load_2d(sB + stage * B_STAGE_BYTES, &map_i, bar_b_full + 8 * stage, colk, row0);
           if (++stage == a.n_stages) {
             stage = 0;
             phase ^= 1;
@@ -275,9 +336,17 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer: D[128 x BN] (+)= A[128 x 8] · B[BN x 8]ᵀ, kind::tf32, fp32 accumulate in TMEM ----
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (lane == 0 && leader) {
+      // ---- MMA issuer: D[128·CTAS x BN] (+)= A[128·CTAS x 8] · B[BN x 8]ᵀ, kind::tf32, fp32 accumulate in TMEM ----
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CTAS) >> 4) << 24);
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if constexpr (PAIR) umma_tf32_pair(d, ad, bd, idesc, acc);
+        else umma_tf32(d, ad, bd, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {
+        if constexpr (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
       if constexpr (!STREAM) {
         mbar_wait(bar_a_full, 0);
         tc_fence_after();
@@ -320,22 +389,22 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           if ((c & 1) == 0) {  // B = hi chunk: hi·hi and lo·hi
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), idesc, accumulate);
+              mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), accumulate);
               accumulate = 1;
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(bb + kk * 32), idesc, 1);
+            for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(bb + kk * 32), 1);
           } else {  // B = lo chunk: hi·lo
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), idesc, 1);
+            for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), 1);
           }
-          umma_commit(bar_b_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+          commit(bar_b_empty + 8 * stage);  // frees the smem slot (of both CTAs of a pair) when these MMAs retire
           if (++stage == a.n_stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(bar_t_full + 8 * as);  // accumulator of this tile complete
+        commit(bar_t_full + 8 * as);  // accumulator of this tile complete (signalled in both CTAs of a pair)
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -435,7 +504,10 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_t_empty + 8 * as);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cta(bar_t_empty + 8 * as, 0);  // the leader's MMA issuer waits for both CTAs' epilogues
+        else mbar_arrive(bar_t_empty + 8 * as);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -496,9 +568,11 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves before everything retired
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -572,8 +646,28 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t co
 static inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 
 // Shared-memory plan for the tensor-core kernel (Kp = contraction width incl. the bias chunk); 0 stages = does not fit.
-static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream) {
+// CTA pairs (cta_group::2) for the resident-user-tile variant: on for long item sweeps, where the halved operand fetch per SM
+// pays (c5, 2 M items: 561 k -> 569 k users/s on the same box; the kernel runs against the power cap, ~1.64 GHz, either way) and
+// off for short ones, where the two cluster barriers and pair scheduling cost more (c2, 63 k items: 22.03 M -> 21.54 M users/s).
+// TGCN_EVAL_PAIR=0 / 1 (read once per process) forces it off / on.  profiles/r02/README.md.
+constexpr int64_t kPairMinItems = 262144;
+static int pair_mode() {
+  static const int mode = [] {
+    const char* e = getenv("TGCN_EVAL_PAIR");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  return mode;
+}
+static bool pair_wanted(int64_t n_range, int k) {
+  if (k > 40) return false;  // the pair variant is instantiated for the two register-list sizes with EW = 2
+  const int m = pair_mode();
+  return m < 0 ? n_range >= kPairMinItems : m == 1;
+}
+
+static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream, bool want_pair = false, bool* pair = nullptr) {
   *stream = Kp > 128;
+  const bool use_pair = !*stream && want_pair;
+  if (pair) *pair = use_pair;
   const size_t a_bytes = *stream ? 0 : (size_t)(2 * (Kp / TC_CHUNK)) * TC_A_CHUNK_BYTES;
   const size_t fixed = 1024 /*align slack*/ + a_bytes + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
   const size_t budget = 227 * 1024;
@@ -588,7 +682,8 @@ static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream) 
     return e && atoi(e) == 128;
   }();
   if (force_bn128) *bn = 128;
-  const size_t stage = *stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)*bn * 128 : (size_t)*bn * 128;
+  if (use_pair) *bn = 256;  // each CTA's ring holds half of the 256-row tile
+  const size_t stage = *stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)*bn * 128 : (size_t)*bn * 128 / (use_pair ? 2 : 1);
   int s = fixed < budget ? (int)((budget - fixed) / stage) : 0;
   if (s > TC_MAX_STAGES) s = TC_MAX_STAGES;
   *n_stages = s;
@@ -631,11 +726,11 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   const int Kp = tc_padded_k(K, has_bias);
   int bn, n_stages;
   size_t smem;
-  bool stream;
-  tc_plan(Kp, &bn, &n_stages, &smem, &stream);
+  bool stream, pair;
+  tc_plan(Kp, &bn, &n_stages, &smem, &stream, pair_wanted(item_end - item_begin, k), &pair);
   TGCN_REQUIRE(n_stages >= 2, "3xTF32 path does not fit in shared memory for K=%lld", (long long)K);
   {  // the list merge at the end of a sweep borrows the item ring: 128 rows x (score, id) x list capacity
-    const size_t stage_bytes = stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)bn * 128 : (size_t)bn * 128;
+    const size_t stage_bytes = stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)bn * 128 : (size_t)bn * 128 / (pair ? 2 : 1);
     TGCN_REQUIRE((size_t)n_stages * stage_bytes >= (size_t)TC_BM * 2 * 40 * 4, "item ring too small for the list merge");
   }
   const int64_t n_range = item_end - item_begin;
@@ -658,7 +753,7 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   TGCN_CHECK_LAUNCH();
   CUtensorMap map_u, map_i;
   if (int rc = make_map(&map_u, u2, n_rank, 2 * (int64_t)Kp, TC_BM)) return rc;
-  if (int rc = make_map(&map_i, i2, n_range, 2 * (int64_t)Kp, bn)) return rc;
+  if (int rc = make_map(&map_i, i2, n_range, 2 * (int64_t)Kp, pair ? bn / 2 : bn)) return rc;
   TcArgs a;
   a.n_rank = (int)n_rank;
   a.K = Kp;
@@ -679,12 +774,34 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   a.out_ids = d_out_ids;
   a.out_scores = d_out_scores;
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
+  if (pair) grid.x = (grid.x + 1) / 2 * 2;  // whole CTA pairs (a trailing CTA without users only lends its half of the item tile)
 #define TGCN_TC_LAUNCH(BN_, KL_, EW_, ST_)                                                                                   \
   do {                                                                                                                       \
     TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     eval_topk_tc_kernel<BN_, KL_, EW_, ST_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                          \
   } while (0)
-  if (stream && bn == 256) {
+#define TGCN_TC_LAUNCH_PAIR(KL_)                                                                                             \
+  do {                                                                                                                       \
+    auto kern = eval_topk_tc_kernel<256, KL_, 2, false, 2>;                                                                  \
+    TGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+    cudaLaunchConfig_t cfg = {};                                                                                             \
+    cfg.gridDim = grid;                                                                                                      \
+    cfg.blockDim = dim3(128 + 128 * 2);                                                                                      \
+    cfg.dynamicSmemBytes = smem;                                                                                             \
+    cfg.stream = s;                                                                                                          \
+    cudaLaunchAttribute attr[1];                                                                                             \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                        \
+    attr[0].val.clusterDim.x = 2;                                                                                            \
+    attr[0].val.clusterDim.y = 1;                                                                                            \
+    attr[0].val.clusterDim.z = 1;                                                                                            \
+    cfg.attrs = attr;                                                                                                        \
+    cfg.numAttrs = 1;                                                                                                        \
+    TGCN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_u, map_i, a));                                                        \
+  } while (0)
+  if (pair) {
+    if (k <= 20) TGCN_TC_LAUNCH_PAIR(20);
+    else TGCN_TC_LAUNCH_PAIR(40);
+  } else if (stream && bn == 256) {
     if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2, true);
     else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2, true);
     else TGCN_TC_LAUNCH(256, 64, 1, true);
@@ -702,6 +819,7 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
     else TGCN_TC_LAUNCH(128, 64, 1, false);
   }
 #undef TGCN_TC_LAUNCH
+#undef TGCN_TC_LAUNCH_PAIR
   TGCN_CHECK_LAUNCH();
   *n_splits_out = n_splits;
   *part_ids_out = part_ids;

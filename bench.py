@@ -314,9 +314,20 @@ def metrics_leg(ops, ids, n_users, n_items, k, dev, flush, torch, sample=20000):
             "sample_rows_checked": sample, "sample_max_abs_err": float((vals - want).abs().max())}
 
 
-def eval_roofline(tensor_flops_per_gpu, ms):
-    """Tensor-pipe roofline of the fused eval call on one GPU: 3 TF32 MMAs per product (3xTF32), against the nominal dense TF32
-    peak and against half the MEASURED dense bf16 rate (MEASURED_PEAKS.json; cuBLAS 8192^3, the only measured tensor figure)."""
+EVAL_PATHS = {
+    "screen": (1, "screen_prep_items_kernel + [gather_rows_kernel] + eval_topk_tc_kernel<SCREEN> (one TF32 tcgen05.mma per product on the raw "
+                  "tables, TMEM accumulators, TMA operands, CTA pairs; exact fp32 re-scoring + certificate in the kernel) + device-gated "
+                  "3xTF32 second pass for uncertified rows"),
+    "3xtf32": (3, "tf32_split_kernel x2 + eval_topk_tc_kernel (3xTF32 tcgen05.mma, TMEM accumulators, TMA operands) + topk_merge_kernel"),
+    "fp32": (0, "eval_topk_simt_kernel (exact fp32 FMA) + topk_merge_kernel"),
+}
+
+
+def eval_roofline(tensor_flops_per_gpu, ms, mma_per_product=3):
+    """Tensor-pipe roofline of the fused eval call on one GPU: the TF32 MMA flops the call EXECUTES (3 per product for 3xTF32, 1 for
+    the screened path) against the nominal dense TF32 peak and against half the MEASURED dense bf16 rate (MEASURED_PEAKS.json; cuBLAS
+    8192^3, the only measured tensor figure).  The screened path is bound by its epilogue (the per-score maximum scan and the list
+    updates), not by the tensor pipe: its fraction is lower although the call is faster."""
     ach = tensor_flops_per_gpu / (ms * 1e-3) / 1e12
     half_bf16 = None
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -326,8 +337,9 @@ def eval_roofline(tensor_flops_per_gpu, ms):
     return {"bound": "tensor", "achieved": ach, "peak": TF32_DENSE_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / TF32_DENSE_PEAK_TFLOPS,
             "peak_source": "nominal dense TF32 (2.25 PFLOP/s bf16 / 2)", "frac_of_half_measured_bf16": (ach / half_bf16) if half_bf16 else None,
             "per_gpu": True, "traffic": None,
-            "note": "achieved = 3 x 2 x K x n_items x n_users TF32 flops / CUDA-event time of the whole call (tf32_split_kernel x2 + "
-                    "eval_topk_tc_kernel [+ topk_merge_kernel]), per GPU"}
+            "mma_per_product": mma_per_product,
+            "note": f"achieved = {mma_per_product} x 2 x K x n_items x n_users TF32 flops / CUDA-event time of the whole call (every kernel "
+                    "of the call), per GPU"}
 
 
 def norm_rel_err(a, b, torch, chunk=1 << 22):
@@ -392,10 +404,15 @@ def c2_leg(args, dev, flush, torch, hbm_peak):
         del stage
     if not args.no_eval:
         users = torch.arange(nu, dtype=torch.int32, device=dev)
+        st = {}
+        ops.eval_topk(graph, out[:nu], out[nu:], k, users=users, stats=st)
+        mma = EVAL_PATHS[st["precision"]][0]
         te = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], k, users=users), args.eval_steps, 1, flush, torch)
         ems = sum(te) / len(te)
-        res["eval"] = {"users_per_s": nu / (ems * 1e-3), "ms": ems, "k": k, "n_users_ranked": nu,
-                       "tensor_flops_per_s": 3 * 2.0 * d * ni * nu / (ems * 1e-3), "roofline": eval_roofline(3 * 2.0 * d * ni * nu, ems)}
+        res["eval"] = {"users_per_s": nu / (ems * 1e-3), "ms": ems, "k": k, "n_users_ranked": nu, "precision": st["precision"],
+                       "second_pass_rows": st["second_pass_rows"], "kernel": EVAL_PATHS[st["precision"]][1],
+                       "tensor_flops_per_s": mma * 2.0 * d * ni * nu / (ems * 1e-3),
+                       "roofline": eval_roofline(mma * 2.0 * d * ni * nu, ems, mma)}
         n_f = min(nu, 32768)
         tf = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], k, users=users[:n_f].contiguous(), precision="fp32"),
                          1, 1, flush, torch)
@@ -961,14 +978,24 @@ def main():
         ev_ms = torch.tensor([sum(t_ev) / len(t_ev)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ev_ms, op=dist.ReduceOp.MAX)
+        prec = ops.eval_resolve_precision(ni, d, k)  # which path the call takes (auto precision)
+        mma = EVAL_PATHS[prec][0]
         ev = {"users_per_s": n_eval / (float(ev_ms) * 1e-3), "k": k, "n_users_ranked": n_eval, "n_items": ni,
-              "ms": float(ev_ms), "score_flops_per_s": 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3),
-              "kernel": "tf32_split_kernel x2 + eval_topk_tc_kernel (3xTF32 tcgen05.mma, TMEM accumulators, TMA operands) + "
-                        "topk_merge_kernel",
-              "tensor_flops_per_s": 3 * 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3), "scaling": "strong",
+              "ms": float(ev_ms), "score_flops_per_s": 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3), "precision": prec,
+              "kernel": EVAL_PATHS[prec][1],
+              "tensor_flops_per_s": mma * 2.0 * d * ni * n_eval / (float(ev_ms) * 1e-3), "scaling": "strong",
               "sharding": "single GPU" if world == 1 else f"user range x{world} (comm-free); item-range variant in eval_item_sharded"}
-        ev["roofline"] = eval_roofline(3 * 2.0 * d * ni * n_eval / world, float(ev_ms))
+        ev["roofline"] = eval_roofline(mma * 2.0 * d * ni * n_eval / world, float(ev_ms), mma)
         if world == 1:
+            st = {}
+            ops.eval_topk(graph, emb[:nu], emb[nu:], k, users=users, stats=st)
+            ev["second_pass_rows"] = st["second_pass_rows"]
+            if prec == "screen":  # the 3xTF32 variant on the same users, for comparison
+                t_3 = timed_steps(lambda: ops.eval_topk(graph, emb[:nu], emb[nu:], k, users=users, precision="3xtf32"),
+                                  max(1, args.eval_steps - 1), 1, flush, torch)
+                ms3 = sum(t_3) / len(t_3)
+                ev["3xtf32"] = {"users_per_s": n_eval / (ms3 * 1e-3), "ms": ms3, "tensor_flops_per_s": 3 * 2.0 * d * ni * n_eval / (ms3 * 1e-3),
+                                "roofline": eval_roofline(3 * 2.0 * d * ni * n_eval, ms3, 3)}
             n_f = min(n_eval, 32768)
             users_f = users[:n_f].contiguous()
             t_f = timed_steps(lambda: ops.eval_topk(graph, emb[:nu], emb[nu:], k, users=users_f, precision="fp32"),

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TGCN_ABI_VERSION 2
+#define TGCN_ABI_VERSION 3
 #define TGCN_MAX_LAYERS 15
 #define TGCN_MAX_PEERS 8
 #define TGCN_MAX_TOPK 128
@@ -205,9 +205,20 @@ int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch,
  * precision: 1 = exact fp32 FMA (SIMT kernel); 2 = 3xTF32 on the tcgen05 tensor cores (k <= 64; K is zero-padded to whole
  * 32-wide chunks, bias terms ride in one extra chunk; the user tile stays resident in shared memory for K <= 128 and is
  * streamed with the item tile above that; scores within ~1e-6 norm-wise of fp32, bit-exact for TF32-representable
- * inputs); 0 = 3xTF32 when eligible, else fp32.
+ * inputs); 3 = screened (k <= 24, K <= 128, no bias terms): ONE TF32 product per score straight from the fp32 tables keeps the best
+ * 40 items per user by approximate score, every kept item within 2·eps of the approximate k-th best (eps = 2.5e-3·|u|·max|i| bounds
+ * the TF32 error) is re-scored in exact fp32 FMA and the list re-sorted on the exact scores; this is provably the exact top-k unless
+ * the band reaches the end of the 40 — such rows are queued on the device and ranked again by the 3xTF32 variant in the same call
+ * (no host synchronisation: the second pass reads the queue length on the device); 0 = screened when eligible and the item range
+ * is long enough for it to pay (131 072 rows at K = 128, 262 144 at K = 96, 786 432 at K <= 64: shorter sweeps are bound by the list
+ * updates, which a 40-entry list doubles), else 3xTF32 when eligible, else fp32.  tgcn_eval_resolve_precision says what 0 resolves to for a shape.
  * Outputs (n_rank, k) int32 ids and fp32 scores.  k <= TGCN_MAX_TOPK. */
 int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
+/* Byte offset, inside the eval workspace, of the int32 in which a screened call (precision 0 / 3) leaves the number of rows it
+ * sent to its second pass; -1 when the screened path does not apply to this shape.  Diagnostics only (bench, tests). */
+int64_t tgcn_eval_screen_queue_offset(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
+/* The precision (1, 2 or 3) a tgcn_eval_topk call with this shape runs at: `precision` itself unless it is 0 (auto). */
+int32_t tgcn_eval_resolve_precision(int64_t n_items_range, int64_t K, int32_t k, int32_t has_bias, int32_t precision);
 int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users,
                    const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K,
                    int64_t item_begin, int64_t item_end, const float* d_user_bias, const float* d_item_bias,

@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libtgcn_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_TOPK = 128
 ADV_MAX_CANDIDATES = 2048
 
@@ -56,6 +56,8 @@ SIGNATURES = {
     "tgcn_bpr_fwd_bwd": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float,
                                    _P, _P, _P, _P, c_int64, _P]),
     "tgcn_eval_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
+    "tgcn_eval_screen_queue_offset": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
+    "tgcn_eval_resolve_precision": (c_int32, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "tgcn_eval_topk": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
                                  c_int32, c_int32, c_int32, c_int32, _P, _P, _P, c_int64, _P]),
     "tgcn_topk_merge": (c_int32, [_P, c_int64, _P, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P]),

@@ -131,4 +131,13 @@ __device__ __forceinline__ bool sorted_contains(const int* __restrict__ col, int
   return lo < end && __ldg(col + lo) == key;
 }
 
+// What the device-gated second pass of the screened eval path ranks (eval_tc.cu): the first *count entries of the queue `rows`
+// (rank positions whose certificate failed).
+struct TcGate {
+  const int* count;
+  const int* rows;
+  const int* users;  // user id of queue entry j (mask rows)
+  const int* src;    // source row of queue entry j in the user table
+};
+
 }  // namespace tgcn

@@ -30,6 +30,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace tgcn {
@@ -38,6 +40,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_CHUNK = 32;            // fp32 per 128-byte swizzle row
 constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
 constexpr int TC_MAX_STAGES = 8;
+constexpr int kBarBlockBytes = 256;   // mbarriers + the TMEM address slot ((10 + 2·TC_MAX_STAGES)·8 + 16 bytes, rounded up)
 
 struct TcArgs {
   int n_rank, K, n_range, item_begin, k;
@@ -52,6 +55,18 @@ struct TcArgs {
   int finalize;
   int* out_ids;
   float* out_scores;
+  // device-gated re-run (the screened path's exact second pass): rank only the first *n_rank_dev rows, write row m to out_rows[m]
+  const int* n_rank_dev;
+  const int* out_rows;
+  // screened variant: raw fp32 operands (1xTF32 scores), exact fp32 re-scoring of the candidates that matter, certificate
+  int Kr;                         // real contraction width (K is padded to whole 32-wide chunks; TMA zero-fills the pad)
+  const float* ivec;              // item table (row = item id) and its leading dimension, for the exact re-scoring
+  int64_t ldi;
+  float eps_c;                    // |s_tf32 - s| <= eps_c * |u| * |i|
+  const unsigned* max_inorm2;     // bits of max_i |i|^2 over the ranked item range (written by screen_prep_items_kernel)
+  int* fb_mark;                   // per rank row: 1 once the row is queued for the exact second pass
+  int* fb_rows;                   // queue of rank rows whose certificate failed
+  int* fb_count;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -220,6 +235,123 @@ __device__ __forceinline__ void reg_list_insert_lex(float (&ls)[KL], int (&li)[K
   li[0] = top ? id : li[0];
 }
 
+// ---- screened variant: what happens to a row's list after the sweep (called by all EW threads of the row) -------------------
+struct ScreenFin {
+  float* ms;            // [kl] approximate scores of the row's merged list, sorted best-first (in the idle item ring) ...
+  int* mi;              // [kl] ... their item ids (INT_MAX = never filled) ...
+  float* me;            // [kl] ... and room for their exact scores
+  int* mp;              // one int per row
+  const uint8_t* urow;  // the row in the resident user tile: chunk c at + c·16 KB, 16-byte unit q at ((q ^ (t & 7)) << 4)
+  int t, sub, n_sub, bar_id, kl, m, mlo, mhi, split;
+  bool valid;
+};
+
+// exact fp32 score of list entries [lo, hi) — strided over the row's n_sub threads — from the fp32 tables
+__device__ __forceinline__ void screen_rescore(const ScreenFin& f, int lo, int hi, int k4, const float* __restrict__ ivec, int64_t ldi) {
+  const int t7 = f.t & 7;
+  for (int j = lo + f.sub; j < hi; j += f.n_sub) {
+    const float4* ip = reinterpret_cast<const float4*>(ivec + (size_t)f.mi[j] * ldi);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int g0 = 0; g0 < k4; g0 += 8) {
+      float4 iv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) iv[q] = g0 + q < k4 ? __ldg(ip + g0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(f.urow + (size_t)(g0 >> 3) * TC_A_CHUNK_BYTES + ((q ^ t7) << 4));
+        acc[0] = fmaf(x.x, iv[q].x, acc[0]);
+        acc[1] = fmaf(x.y, iv[q].y, acc[1]);
+        acc[2] = fmaf(x.z, iv[q].z, acc[2]);
+        acc[3] = fmaf(x.w, iv[q].w, acc[3]);
+      }
+    }
+    f.me[j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+}
+
+// With eps = eps_c·|u|·max|i| >= |approximate - exact|:  (1) the k best entries by approximate score are re-scored; E = the smallest
+// of their exact scores, so k items score at least E;  (2) an entry whose approximate score + eps is below E cannot be among the k
+// best, nor can any entry after it (the list is sorted) or any item that is not in the full list (it scores at most the last entry):
+// entries are re-scored up to the first such one;  (3) the re-scored entries, sorted on (exact score desc, id asc), start with the
+// exact top-k.  If no entry of a FULL list can be ruled out, an item outside the list might belong to the k best: the row is queued
+// for the second pass.
+__device__ __noinline__ void screen_finalize(const ScreenFin f, int Kr, int k, const float* __restrict__ ivec, int64_t ldi, float eps_c,
+                                             const unsigned* __restrict__ max_inorm2, int* fb_mark, int* fb_rows, int* fb_count, int direct,
+                                             int finalize, const int* __restrict__ mcol, int mcol_off, int n_rank_stride,
+                                             const int* __restrict__ out_rows, int* out_ids, float* out_scores, int* part_ids,
+                                             float* part_scores) {
+  const int k4 = Kr >> 2, t7 = f.t & 7;
+  int n_valid = 0;
+  float eps = 0.f;
+  if (f.sub == 0) {
+    float un2 = 0.f;
+    for (int g = 0; g < k4; ++g) {
+      const float4 x = *reinterpret_cast<const float4*>(f.urow + (size_t)(g >> 3) * TC_A_CHUNK_BYTES + (((g & 7) ^ t7) << 4));
+      un2 = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, un2))));
+    }
+    eps = eps_c * sqrtf(un2) * sqrtf(__uint_as_float(__ldg(max_inorm2)));
+    while (n_valid < f.kl && f.mi[n_valid] != INT_MAX) ++n_valid;
+    *f.mp = n_valid < k ? n_valid : k;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(f.bar_id), "r"(32 * f.n_sub) : "memory");
+  const int P1 = *f.mp;
+  screen_rescore(f, 0, P1, k4, ivec, ldi);
+  asm volatile("bar.sync %0, %1;" ::"r"(f.bar_id), "r"(32 * f.n_sub) : "memory");
+  bool flagged = false;
+  if (f.sub == 0) {
+    int P = P1;
+    if (n_valid >= k) {
+      float E = INFINITY;
+      for (int j = 0; j < k; ++j) E = fminf(E, f.me[j]);
+      while (P < n_valid && f.ms[P] + eps >= E) ++P;
+      flagged = f.valid && ((P == f.kl) || !(eps < INFINITY));
+    }
+    *f.mp = P;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(f.bar_id), "r"(32 * f.n_sub) : "memory");
+  const int P = *f.mp;
+  screen_rescore(f, P1, P, k4, ivec, ldi);
+  asm volatile("bar.sync %0, %1;" ::"r"(f.bar_id), "r"(32 * f.n_sub) : "memory");
+  if (f.sub != 0 || !f.valid) return;
+  for (int j = 1; j < P; ++j) {  // insertion sort on (exact score desc, id asc)
+    const float s = f.me[j];
+    const int id = f.mi[j];
+    int q = j;
+    while (q > 0 && ranks_before(s, id, f.me[q - 1], f.mi[q - 1])) {
+      f.me[q] = f.me[q - 1];
+      f.mi[q] = f.mi[q - 1];
+      --q;
+    }
+    f.me[q] = s;
+    f.mi[q] = id;
+  }
+  if (flagged && atomicExch(fb_mark + f.m, 1) == 0) fb_rows[atomicAdd(fb_count, 1)] = f.m;
+  const int real = P < k ? P : k;  // P < k only when fewer than k items could be ranked at all
+  if (direct) {
+    const size_t o = (size_t)(out_rows ? __ldg(out_rows + f.m) : f.m) * k;
+    for (int j = 0; j < k; ++j) {
+      int id = j < real ? f.mi[j] : -1;
+      float s = j < real ? f.me[j] : -INFINITY;
+      if (j >= real) {
+        if (finalize) {  // fewer than k rankable items: complete with train items, lowest id first (G9)
+          const int tt = j - real;
+          id = tt < f.mhi - f.mlo ? __ldg(mcol + f.mlo + tt) - mcol_off : -1;
+        } else {
+          id = INT_MAX;
+        }
+      }
+      out_ids[o + j] = id;
+      out_scores[o + j] = s;
+    }
+  } else {
+    const size_t o = ((size_t)f.split * n_rank_stride + f.m) * k;
+    for (int j = 0; j < k; ++j) {
+      part_ids[o + j] = j < real ? f.mi[j] : INT_MAX;
+      part_scores[o + j] = j < real ? f.me[j] : -INFINITY;
+    }
+  }
+}
+
 // BN = item rows per tile, KL = list capacity (>= k), EW = epilogue warps per TMEM lane quarter: warp `sub` of a quarter
 // scans columns [sub·BN/EW, (sub+1)·BN/EW) of every tile for the quarter's 32 user rows.
 // STREAM = false: the user tile [hi | lo] stays resident in shared memory for the whole sweep (K <= 128).
@@ -228,18 +360,36 @@ __device__ __forceinline__ void reg_list_insert_lex(float (&ls)[KL], int (&li)[K
 // CTAS = 2 (non-streamed only): CTA pairs (cluster of 2 along x) — every MMA covers 256 users x BN items, the item tile is split
 //                 between the two CTAs' rings (BN / 2 rows each), so the shared-memory operand fetch per SM and the number of MMA
 //                 instructions per score both halve.  Each CTA keeps its own users' accumulator rows, lists and epilogue.
-template <int BN, int KL, int EW, bool STREAM, int CTAS = 1>
+// SCREEN (non-streamed only): the operands are the RAW fp32 tables (no hi/lo split) and every score is ONE TF32 product — a third of
+//                 the tensor work.  The tensor core reads the upper 19 bits of each fp32, so |s_tf32 - s| <= eps = eps_c·|u|·|i|
+//                 (2·2^-10 from the two truncations + accumulation, Cauchy-Schwarz over the products).  The sweep keeps the best
+//                 KL > k items by the APPROXIMATE score; afterwards every kept item within 2·eps of the approximate k-th best is
+//                 re-scored in exact fp32 FMA from the tables and the list is re-sorted on the exact scores.  An item outside
+//                 that band has an exact score below at least k re-scored ones, so the result is the exact top-k PROVIDED the band
+//                 ends inside the list; a row whose band reaches the list's last entry (an excluded item might belong to it) is
+//                 queued in fb_rows and ranked again by the 3xTF32 variant (eval_topk_tc, second pass gated on the device).
+// NACC = accumulator stages in tensor memory (NACC·BN <= 512 columns): 2 lets the epilogue of one tile overlap the MMAs of the next;
+//                 4 (BN = 128) lets a warp that updates lists in one tile catch up over the next three before the MMA issuer, which
+//                 waits for the slowest epilogue warp of the stage it is about to overwrite, has to wait for it — measured on the
+//                 screened pair variant and NOT adopted: c5 163.9 ms against 129.3 ms with two stages of 256 columns (the 128-column
+//                 MMA costs nearly as much per instruction as the 256-column one; profiles/r02/README.md).
+template <int BN, int KL, int EW, bool STREAM, int CTAS = 1, bool SCREEN = false, int NACC = 2>
 __global__ void __launch_bounds__(128 + 128 * EW, 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
   static_assert(CTAS == 1 || (CTAS == 2 && !STREAM), "CTA pairs are implemented for the resident-user-tile variant");
+  static_assert(!SCREEN || !STREAM, "screening is implemented for the resident-user-tile variant");
+  static_assert(NACC * BN <= 512 && (NACC == 2 || NACC == 4), "tensor memory holds 512 accumulator columns");
   constexpr bool PAIR = CTAS == 2;
+  int n_rank = a.n_rank;
+  if (a.n_rank_dev) n_rank = min(n_rank, __ldg(a.n_rank_dev));
+  if ((int)(blockIdx.x / CTAS * CTAS) * TC_BM >= n_rank) return;  // (a whole pair leaves together)
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const int KC = a.K / TC_CHUNK;
-  const int n_a = STREAM ? 0 : 2 * KC;  // resident user chunks
+  const int n_a = STREAM ? 0 : (SCREEN ? KC : 2 * KC);  // resident user chunks
   constexpr int BROWS = BN / CTAS;  // item rows of a tile held by THIS CTA's ring
   constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BN * 128 : BROWS * 128;
   const uint32_t sA = base;
@@ -249,9 +399,9 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   const uint32_t bar_a_full = smem_u32(bars + 0);
   const uint32_t bar_b_full = smem_u32(bars + 1);                      // [TC_MAX_STAGES]
   const uint32_t bar_b_empty = smem_u32(bars + 1 + TC_MAX_STAGES);     // [TC_MAX_STAGES]
-  const uint32_t bar_t_full = smem_u32(bars + 1 + 2 * TC_MAX_STAGES);  // [2]
-  const uint32_t bar_t_empty = smem_u32(bars + 3 + 2 * TC_MAX_STAGES); // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_MAX_STAGES);
+  const uint32_t bar_t_full = smem_u32(bars + 1 + 2 * TC_MAX_STAGES);  // [4]
+  const uint32_t bar_t_empty = smem_u32(bars + 5 + 2 * TC_MAX_STAGES); // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * TC_MAX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
@@ -269,7 +419,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       mbar_init(bar_b_full + 8 * s, 1);
       mbar_init(bar_b_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(bar_t_full + 8 * s, 1);
       mbar_init(bar_t_empty + 8 * s, 4 * EW * CTAS);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
     }
@@ -278,10 +428,10 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers exist before anyone (TMA of the peer, remote arrives) touches them
   if (warp == 2) {
     if constexpr (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NACC * BN) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NACC * BN) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
@@ -321,8 +471,8 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       }
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int row0 = tile * BN + (int)cta_rank * BROWS;  // pair: this CTA streams its half of the item tile
-        for (int c = 0; c < n_a; ++c) {  // order: hi_0, lo_0, hi_1, lo_1, ...
-          const int colk = (c & 1) ? a.K + (c >> 1) * TC_CHUNK : (c >> 1) * TC_CHUNK;
+        for (int c = 0; c < n_a; ++c) {  // order: hi_0, lo_0, hi_1, lo_1, ...  (screened: the raw chunks in order)
+          const int colk = SCREEN ? c * TC_CHUNK : ((c & 1) ? a.K + (c >> 1) * TC_CHUNK : (c >> 1) * TC_CHUNK);
           mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);   // own barrier: the MMA commit is multicast to both CTAs
           if (leader) mbar_expect_tx(bar_b_full + 8 * stage, CTAS * B_STAGE_BYTES);
           if constexpr (PAIR) tma_load_2d_pair(sB + stage * B_STAGE_BYTES, &map_i, bar_b_full + 8 * stage, colk, row0);
@@ -384,9 +534,15 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           mbar_wait(bar_b_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t bb = sB + stage * B_STAGE_BYTES;
-          const int kc = c >> 1;
+          const int kc = SCREEN ? c : c >> 1;
           const uint32_t a_hi = sA + kc * TC_A_CHUNK_BYTES, a_lo = sA + (KC + kc) * TC_A_CHUNK_BYTES;
-          if ((c & 1) == 0) {  // B = hi chunk: hi·hi and lo·hi
+          if constexpr (SCREEN) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), accumulate);
+              accumulate = 1;
+            }
+          } else if ((c & 1) == 0) {  // B = hi chunk: hi·hi and lo·hi
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(bb + kk * 32), accumulate);
@@ -405,7 +561,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           }
         }
         commit(bar_t_full + 8 * as);  // accumulator of this tile complete (signalled in both CTAs of a pair)
-        if (++as == 2) {
+        if (++as == NACC) {
           as = 0;
           aphase ^= 1;
         }
@@ -420,7 +576,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
     const int sub = (warp - 4) >> 2;  // which column slice of every tile this warp scans
     const int t = ew * 32 + lane;
     const int m = m0 + t;
-    const bool valid = m < a.n_rank;
+    const bool valid = m < n_rank;
     const int user = valid ? (a.users ? __ldg(a.users + m) : m) : 0;
     TGCN_DASSERT(!valid || !a.mrowptr || user >= a.mrow_begin);
     int mlo = 0, mhi = 0;
@@ -508,7 +664,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         if constexpr (PAIR) mbar_arrive_cta(bar_t_empty + 8 * as, 0);  // the leader's MMA issuer waits for both CTAs' epilogues
         else mbar_arrive(bar_t_empty + 8 * as);
       }
-      if (++as == 2) {
+      if (++as == NACC) {
         as = 0;
         aphase ^= 1;
       }
@@ -537,12 +693,45 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EW) : "memory");
       }
     }
+    if constexpr (SCREEN) {
+      // ---- exact re-scoring of the band around the k-th best, certificate and output (see the template comment): a separate
+      // function with its own registers, so that none of it weighs on the sweep above; the lists travel through the idle ring
+      asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(128 * EW) : "memory");  // every quarter's merge is over: the ring is re-laid out
+      float* ms = reinterpret_cast<float*>(ring) + (size_t)t * (3 * KL);
+      int* mi = reinterpret_cast<int*>(ms + KL);
+      if (sub == 0) {
+#pragma unroll
+        for (int j = 0; j < KL; ++j) {
+          ms[j] = ls[j];
+          mi[j] = li[j];
+        }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EW) : "memory");
+      ScreenFin f;
+      f.ms = ms;
+      f.mi = mi;
+      f.me = ms + 2 * KL;
+      f.mp = reinterpret_cast<int*>(ring + (size_t)TC_BM * 3 * KL * 4) + t;
+      f.urow = gen_base + (size_t)t * 128;
+      f.t = t;
+      f.sub = sub;
+      f.n_sub = EW;
+      f.bar_id = 1 + ew;
+      f.kl = KL;
+      f.m = m;
+      f.valid = valid;
+      f.mlo = mlo;
+      f.mhi = mhi;
+      f.split = blockIdx.y;
+      screen_finalize(f, a.Kr, a.k, a.ivec, a.ldi, a.eps_c, a.max_inorm2, a.fb_mark, a.fb_rows, a.fb_count, a.direct, a.finalize, a.mcol, a.mcol_off,
+                      a.n_rank, a.out_rows, a.out_ids, a.out_scores, a.part_ids, a.part_scores);
+    } else {
     const bool writer = valid && sub == 0;
     if (writer && a.direct) {
       int real = 0;  // the list is sorted, so sentinels (never-filled slots) come last
 #pragma unroll
       for (int j = 0; j < KL; ++j) real += li[j] != INT_MAX ? 1 : 0;
-      const size_t o = (size_t)m * a.k;
+      const size_t o = (size_t)(a.out_rows ? __ldg(a.out_rows + m) : m) * a.k;
 #pragma unroll
       for (int j = 0; j < KL; ++j)
         if (j < a.k) {
@@ -565,14 +754,15 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           a.part_scores[o + j] = ls[j];
         }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves before everything retired
   if (warp == 2) {
     tc_fence_after();
-    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NACC * BN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NACC * BN) : "memory");
   }
 }
 
@@ -582,11 +772,16 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
 __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict__ src, int64_t ld, const int* __restrict__ rows,
                                                          int64_t row_begin, int64_t n_rows, int K, int Kp,
                                                          const float* __restrict__ bias, const int* __restrict__ bias_rows,
-                                                         int64_t bias_begin, int item_side, int bias_chunk, float* __restrict__ out) {
+                                                         int64_t bias_begin, int item_side, int bias_chunk, float* __restrict__ out,
+                                                         const int* __restrict__ gate, int gate_rows) {
   const int k4 = Kp >> 2;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n_rows * k4) return;
   const int64_t r = t / k4;
+  if (gate) {  // device-gated second pass: only the first *gate rows (gate_rows) / nothing at all when *gate == 0
+    const int c = __ldg(gate);
+    if (gate_rows ? r >= c : c == 0) return;
+  }
   const int c = (int)(t % k4) * 4;
   float xs[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < K) {
@@ -615,6 +810,56 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict
   *reinterpret_cast<float4*>(out + r * 2 * Kp + Kp + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// Screened variant, item side: out (n_rows, K) = rna_tf32(src rows) — the tensor core then reads exactly these values, so the item
+// operand is off by at most 2^-11 relative instead of the 2^-10 of a 19-bit truncation — and the max |row|^2 of the exact rows.
+__global__ void __launch_bounds__(256) screen_prep_items_kernel(const float* __restrict__ src, int64_t ld, int64_t row_begin, int64_t n_rows,
+                                                                int K, float* __restrict__ out, unsigned* __restrict__ max_norm2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float best = 0.f;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const float* row = src + (row_begin + r) * ld;
+    float acc = 0.f;
+    for (int c = lane * 4; c < K; c += 128) {
+      const float4 x = ldg4(row + c);
+      acc = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, acc))));
+      uint32_t h[4];
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[0]) : "f"(x.x));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[1]) : "f"(x.y));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[2]) : "f"(x.z));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[3]) : "f"(x.w));
+      *reinterpret_cast<uint4*>(out + r * K + c) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    best = fmaxf(best, acc);
+  }
+  if (lane == 0 && best > 0.f) atomicMax(max_norm2, __float_as_uint(best * 1.0001f));  // (any summation order stays below the bound)
+}
+
+// out (n_rows, K) = src[rows[r], :K]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int64_t ld, const int* __restrict__ rows, int64_t n_rows,
+                                                          int K, float* __restrict__ out) {
+  const int k4 = K >> 2;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_rows * k4) return;
+  const int64_t r = t / k4;
+  const int c = (int)(t % k4) * 4;
+  *reinterpret_cast<float4*>(out + r * K + c) = ldg4(src + (int64_t)__ldg(rows + r) * ld + c);
+}
+
+// the queue of rank rows the screen could not certify -> the user ids (mask rows) and source rows of the second pass
+__global__ void __launch_bounds__(256) fb_index_kernel(const int* __restrict__ fb_rows, const int* __restrict__ fb_count,
+                                                       const int* __restrict__ users, int by_pos, int n_rank, int* __restrict__ fb_users,
+                                                       int* __restrict__ fb_src) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= min(n_rank, __ldg(fb_count))) return;
+  const int pos = __ldg(fb_rows + j);
+  const int user = users ? __ldg(users + pos) : pos;
+  fb_users[j] = user;
+  fb_src[j] = (by_pos || !users) ? pos : user;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -630,11 +875,11 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int box_rows) {
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int box_rows, int64_t ld = 0) {
   EncodeTiledFn fn = encode_fn();
   TGCN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : cols) * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)TC_CHUNK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -669,7 +914,7 @@ static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream, 
   const bool use_pair = !*stream && want_pair;
   if (pair) *pair = use_pair;
   const size_t a_bytes = *stream ? 0 : (size_t)(2 * (Kp / TC_CHUNK)) * TC_A_CHUNK_BYTES;
-  const size_t fixed = 1024 /*align slack*/ + a_bytes + (6 + 2 * TC_MAX_STAGES) * 8 + 16;
+  const size_t fixed = 1024 /*align slack*/ + a_bytes + kBarBlockBytes;
   const size_t budget = 227 * 1024;
   // 256-row item tiles whenever three ring stages still fit beside the resident user tile: a 128x128x8 TF32 MMA was
   // measured at ~117 cycles against 64 ideal (issue overhead per instruction), so wide tiles matter more than ring depth
@@ -710,18 +955,115 @@ int eval_tc_tile_n(int64_t K, bool has_bias) {
   return bn;
 }
 
-int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, bool has_bias, int n_splits) {
-  const int64_t Kp = tc_padded_k(K, has_bias);
-  return al256(n_rank * 2 * Kp * 4) + al256(n_range * 2 * Kp * 4) + al256((int64_t)n_splits * n_rank * k * 4) * 2 + 256;
-}
-
+// ---- workspace layout (one place) --------------------------------------------------------------------------------
+// [u2 | i2 | ctrl (count, max |i|^2) + fb_mark | fb_rows | fb_users | fb_src | part_ids | part_scores]
+// The partial tables come last and are sized for the larger of the caller's split count and the second pass's (tc_fb_split_plan),
+// so the two passes of a screened call agree on where everything before them lives.
+constexpr int kFbSplits = 8;
 void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_splits, int* tiles_per_split);
 
+// Item splits of the device-gated second pass: it usually ranks a handful of rows, so a lone CTA would sweep the whole range.
+static void tc_fb_split_plan(int64_t n_rank, int64_t n_range, int bn, int* n_splits, int* tps) {
+  eval_split_plan(n_rank, n_range, bn, n_splits, tps);
+  const int64_t n_tiles = (n_range + bn - 1) / bn;
+  int64_t want = n_tiles / 32;
+  if (want > kFbSplits) want = kFbSplits;
+  if (want > *n_splits) {
+    *tps = (int)((n_tiles + want - 1) / want);
+    *n_splits = (int)((n_tiles + *tps - 1) / *tps);
+  }
+}
+
+struct TcWorkspace {
+  float *u2, *i2;
+  int* part_ids;
+  float* part_scores;
+  int* ctrl;  // [0] = queue length, [1] = bits of max |i|^2; fb_mark follows at +64 ints (one memset clears both)
+  int *fb_mark, *fb_rows, *fb_users, *fb_src;
+  int64_t bytes;
+};
+
+static TcWorkspace tc_workspace(void* base, int64_t n_rank, int64_t n_range, int64_t Kp, int32_t k, int n_splits) {
+  int fs, fs2, ftps;
+  tc_fb_split_plan(n_rank, n_range, 256, &fs, &ftps);
+  tc_fb_split_plan(n_rank, n_range, 128, &fs2, &ftps);
+  const int64_t ns = std::max<int64_t>(n_splits, std::max(fs, fs2));
+  TcWorkspace w;
+  char* p = (char*)base;
+  auto take = [&](int64_t bytes) {
+    char* r = p;
+    p += al256(bytes);
+    return r;
+  };
+  w.u2 = (float*)take(n_rank * 2 * Kp * 4);
+  w.i2 = (float*)take(n_range * 2 * Kp * 4);
+  w.ctrl = (int*)take(256 + n_rank * 4);
+  w.fb_mark = w.ctrl + 64;
+  w.fb_rows = (int*)take(n_rank * 4);
+  w.fb_users = (int*)take(n_rank * 4);
+  w.fb_src = (int*)take(n_rank * 4);
+  w.part_ids = (int*)take(ns * n_rank * k * 4);
+  w.part_scores = (float*)take(ns * n_rank * k * 4);
+  w.bytes = (int64_t)(p - (char*)base) + 256;
+  return w;
+}
+
+int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, bool has_bias, int n_splits) {
+  return tc_workspace(nullptr, n_rank, n_range, tc_padded_k(K, has_bias), k, n_splits).bytes;
+}
+
+
+template <int BN, int KL, int EW, bool ST, int CTAS, bool SCREEN, int NACC = 2>
+static int tc_launch(dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& map_u, const CUtensorMap& map_i, const TcArgs& a) {
+  auto kern = eval_topk_tc_kernel<BN, KL, EW, ST, CTAS, SCREEN, NACC>;
+  TGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(128 + 128 * EW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTAS > 1 ? 1 : 0;
+  TGCN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_u, map_i, a));
+  return 0;
+}
+
+static void tc_args_common(TcArgs* a, int64_t n_rank, int Kp, int64_t K, int64_t n_range, int64_t item_begin, int32_t k, int tps, int n_stages,
+                           const int* users, const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, const TcWorkspace& w,
+                           int n_splits, int finalize, int* d_out_ids, float* d_out_scores) {
+  *a = TcArgs{};
+  a->n_rank = (int)n_rank;
+  a->K = Kp;
+  a->Kr = (int)K;
+  a->n_range = (int)n_range;
+  a->item_begin = (int)item_begin;
+  a->k = k;
+  a->tiles_per_split = tps;
+  a->n_stages = n_stages;
+  a->users = users;
+  a->mrowptr = mrowptr;
+  a->mcol = mcol;
+  a->mrow_begin = mrow_begin;
+  a->mcol_off = mcol_off;
+  a->part_ids = w.part_ids;
+  a->part_scores = w.part_scores;
+  a->direct = n_splits == 1;
+  a->finalize = finalize;
+  a->out_ids = d_out_ids;
+  a->out_scores = d_out_scores;
+}
+
+// The 3xTF32 variant.  gate != nullptr: the second pass of the screened path — every kernel reads the queue length on the device.
 int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users,
                  int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
                  int64_t item_end, const float* d_user_bias, const float* d_item_bias, int32_t k, int finalize, int* d_out_ids,
                  float* d_out_scores, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
-                 float** part_scores_out, cudaStream_t s) {
+                 float** part_scores_out, cudaStream_t s, const TcGate* gate) {
   const bool has_bias = d_user_bias != nullptr || d_item_bias != nullptr;
   const int Kp = tc_padded_k(K, has_bias);
   int bn, n_stages;
@@ -735,95 +1077,178 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   }
   const int64_t n_range = item_end - item_begin;
   int n_splits, tps;
-  eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
-  const int64_t need = eval_tc_workspace_bytes(n_rank, n_range, K, k, has_bias, n_splits);
-  TGCN_REQUIRE(d_workspace && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
-  char* ws = (char*)d_workspace;
-  float* u2 = (float*)ws;
-  float* i2 = (float*)(ws + al256(n_rank * 2 * (int64_t)Kp * 4));
-  int* part_ids = (int*)((char*)i2 + al256(n_range * 2 * (int64_t)Kp * 4));
-  float* part_scores = (float*)((char*)part_ids + al256((int64_t)n_splits * n_rank * k * 4));
+  if (gate) tc_fb_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  else eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  const TcWorkspace w = tc_workspace(d_workspace, n_rank, n_range, Kp, k, n_splits);
+  TGCN_REQUIRE(d_workspace && workspace_bytes >= w.bytes, "workspace too small: need %lld bytes", (long long)w.bytes);
+  float *u2 = w.u2, *i2 = w.i2;
   const int k4 = Kp / 4;
   // user operand: rows gathered by user id unless already packed in list order; user bias follows the same indexing
-  tf32_split_kernel<<<(unsigned)((n_rank * k4 + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, by_pos ? nullptr : d_users, 0, n_rank, (int)K, Kp,
-                                                                         d_user_bias, by_pos ? nullptr : d_users, 0, 0, has_bias ? 1 : 0, u2);
+  const int* urows = gate ? gate->src : (by_pos ? nullptr : d_users);
+  tf32_split_kernel<<<(unsigned)((n_rank * k4 + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, urows, 0, n_rank, (int)K, Kp, d_user_bias, urows, 0, 0,
+                                                                         has_bias ? 1 : 0, u2, gate ? gate->count : nullptr, 1);
   TGCN_CHECK_LAUNCH();
   tf32_split_kernel<<<(unsigned)((n_range * k4 + 255) / 256), 256, 0, s>>>(d_item_vecs, ldi, nullptr, item_begin, n_range, (int)K, Kp, d_item_bias,
-                                                                          nullptr, item_begin, 1, has_bias ? 1 : 0, i2);
+                                                                          nullptr, item_begin, 1, has_bias ? 1 : 0, i2,
+                                                                          gate ? gate->count : nullptr, 0);
   TGCN_CHECK_LAUNCH();
   CUtensorMap map_u, map_i;
   if (int rc = make_map(&map_u, u2, n_rank, 2 * (int64_t)Kp, TC_BM)) return rc;
   if (int rc = make_map(&map_i, i2, n_range, 2 * (int64_t)Kp, pair ? bn / 2 : bn)) return rc;
   TcArgs a;
-  a.n_rank = (int)n_rank;
-  a.K = Kp;
-  a.n_range = (int)n_range;
-  a.item_begin = (int)item_begin;
-  a.k = k;
-  a.tiles_per_split = tps;
-  a.n_stages = n_stages;
-  a.users = d_users;
-  a.mrowptr = mrowptr;
-  a.mcol = mcol;
-  a.mrow_begin = mrow_begin;
-  a.mcol_off = mcol_off;
-  a.part_ids = part_ids;
-  a.part_scores = part_scores;
-  a.direct = n_splits == 1;
-  a.finalize = finalize;
-  a.out_ids = d_out_ids;
-  a.out_scores = d_out_scores;
+  tc_args_common(&a, n_rank, Kp, K, n_range, item_begin, k, tps, n_stages, gate ? gate->users : d_users, mrowptr, mcol, mrow_begin, mcol_off, w,
+                 n_splits, finalize, d_out_ids, d_out_scores);
+  if (gate) {
+    a.n_rank_dev = gate->count;
+    a.out_rows = gate->rows;
+  }
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
   if (pair) grid.x = (grid.x + 1) / 2 * 2;  // whole CTA pairs (a trailing CTA without users only lends its half of the item tile)
-#define TGCN_TC_LAUNCH(BN_, KL_, EW_, ST_)                                                                                   \
-  do {                                                                                                                       \
-    TGCN_CHECK_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<BN_, KL_, EW_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    eval_topk_tc_kernel<BN_, KL_, EW_, ST_><<<grid, 128 + 128 * EW_, smem, s>>>(map_u, map_i, a);                          \
-  } while (0)
-#define TGCN_TC_LAUNCH_PAIR(KL_)                                                                                             \
-  do {                                                                                                                       \
-    auto kern = eval_topk_tc_kernel<256, KL_, 2, false, 2>;                                                                  \
-    TGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
-    cudaLaunchConfig_t cfg = {};                                                                                             \
-    cfg.gridDim = grid;                                                                                                      \
-    cfg.blockDim = dim3(128 + 128 * 2);                                                                                      \
-    cfg.dynamicSmemBytes = smem;                                                                                             \
-    cfg.stream = s;                                                                                                          \
-    cudaLaunchAttribute attr[1];                                                                                             \
-    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                        \
-    attr[0].val.clusterDim.x = 2;                                                                                            \
-    attr[0].val.clusterDim.y = 1;                                                                                            \
-    attr[0].val.clusterDim.z = 1;                                                                                            \
-    cfg.attrs = attr;                                                                                                        \
-    cfg.numAttrs = 1;                                                                                                        \
-    TGCN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map_u, map_i, a));                                                        \
-  } while (0)
-  if (pair) {
-    if (k <= 20) TGCN_TC_LAUNCH_PAIR(20);
-    else TGCN_TC_LAUNCH_PAIR(40);
-  } else if (stream && bn == 256) {
-    if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2, true);
-    else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2, true);
-    else TGCN_TC_LAUNCH(256, 64, 1, true);
-  } else if (stream) {
-    if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2, true);
-    else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2, true);
-    else TGCN_TC_LAUNCH(128, 64, 1, true);
-  } else if (bn == 256) {
-    if (k <= 20) TGCN_TC_LAUNCH(256, 20, 2, false);
-    else if (k <= 40) TGCN_TC_LAUNCH(256, 40, 2, false);
-    else TGCN_TC_LAUNCH(256, 64, 1, false);
-  } else {
-    if (k <= 20) TGCN_TC_LAUNCH(128, 20, 2, false);
-    else if (k <= 40) TGCN_TC_LAUNCH(128, 40, 2, false);
-    else TGCN_TC_LAUNCH(128, 64, 1, false);
-  }
-#undef TGCN_TC_LAUNCH
-#undef TGCN_TC_LAUNCH_PAIR
+  int rc;
+  if (pair) rc = k <= 20 ? tc_launch<256, 20, 2, false, 2, false>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 2, false>(grid, smem, s, map_u, map_i, a);
+  else if (stream && bn == 256)
+    rc = k <= 20   ? tc_launch<256, 20, 2, true, 1, false>(grid, smem, s, map_u, map_i, a)
+         : k <= 40 ? tc_launch<256, 40, 2, true, 1, false>(grid, smem, s, map_u, map_i, a)
+                   : tc_launch<256, 64, 1, true, 1, false>(grid, smem, s, map_u, map_i, a);
+  else if (stream)
+    rc = k <= 20   ? tc_launch<128, 20, 2, true, 1, false>(grid, smem, s, map_u, map_i, a)
+         : k <= 40 ? tc_launch<128, 40, 2, true, 1, false>(grid, smem, s, map_u, map_i, a)
+                   : tc_launch<128, 64, 1, true, 1, false>(grid, smem, s, map_u, map_i, a);
+  else if (bn == 256)
+    rc = k <= 20   ? tc_launch<256, 20, 2, false, 1, false>(grid, smem, s, map_u, map_i, a)
+         : k <= 40 ? tc_launch<256, 40, 2, false, 1, false>(grid, smem, s, map_u, map_i, a)
+                   : tc_launch<256, 64, 1, false, 1, false>(grid, smem, s, map_u, map_i, a);
+  else
+    rc = k <= 20   ? tc_launch<128, 20, 2, false, 1, false>(grid, smem, s, map_u, map_i, a)
+         : k <= 40 ? tc_launch<128, 40, 2, false, 1, false>(grid, smem, s, map_u, map_i, a)
+                   : tc_launch<128, 64, 1, false, 1, false>(grid, smem, s, map_u, map_i, a);
+  if (rc) return rc;
   TGCN_CHECK_LAUNCH();
   *n_splits_out = n_splits;
-  *part_ids_out = part_ids;
-  *part_scores_out = part_scores;
+  *part_ids_out = w.part_ids;
+  *part_scores_out = w.part_scores;
+  return 0;
+}
+
+// ---- screened variant -------------------------------------------------------------------------------------------------
+constexpr int kScreenKL = 40;       // list capacity of the screen
+constexpr int kScreenMaxK = 24;     // ... which leaves at least 16 entries of margin below the k-th best
+// experiment switch (read once): TGCN_EVAL_SCREEN_KL = 24 | 32 | 40
+static int screen_kl(int k) {
+  static const int v = [] {
+    const char* e = getenv("TGCN_EVAL_SCREEN_KL");
+    const int x = e ? atoi(e) : 0;
+    return (x == 24 || x == 32 || x == 40) ? x : kScreenKL;
+  }();
+  return v >= k + 4 ? v : kScreenKL;
+}
+// |s_tf32 - s| <= eps_c |u||i|: the user operand (raw fp32, so that the resident tile also serves the exact re-scoring) loses at most
+// 2^-10 of each element to the tensor core's 19-bit read, the item operand (rounded to nearest beforehand) 2^-11: 1.47e-3 on a product
+// with the cross term; the fp32 accumulation of K <= 128 exact products adds < 4e-5 (the 3xTF32 variant, same accumulation, agrees
+// with fp64 to ~1e-6); 1.6e-3 keeps 6 % in hand.  TGCN_EVAL_SCREEN_EPS overrides (experiments: a value too small makes the parity
+// tests fail, a large one sends every row to the second pass).
+static float screen_eps_c() {
+  static const float c = [] {
+    const char* e = getenv("TGCN_EVAL_SCREEN_EPS");
+    const float v = e ? (float)atof(e) : 0.f;
+    return v > 0.f ? v : 1.6e-3f;
+  }();
+  return c;
+}
+
+bool eval_tc_screen_eligible(int64_t K, int32_t k, bool has_bias) {
+  return !has_bias && K % 4 == 0 && K > 0 && tc_padded_k(K, false) <= 128 && k <= kScreenMaxK;
+}
+
+// precision 0 takes the screened path for long item sweeps only: on short ones the kernel is bound by the list updates of the sweep's
+// opening (every item beats an empty list), and a 40-entry list doubles those (c2, 63 k items: 15.0 ms screened, 8.6 ms 3xTF32; c5,
+// 2 M items: 126.6 ms against 271.7 ms).  The screened sweep costs about the same at every width (it is bound by its epilogue), the
+// 3xTF32 one grows with K, so the break-even moves: measured (75 776 users, random embeddings, tools/screen_crossover.py) at
+// ~110 k items for K = 128 and ~600 k for K = 64.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces it off / on where eligible.
+static int64_t screen_min_items(int64_t K) {
+  const int Kp = tc_padded_k(K, false);
+  return Kp >= 128 ? 131072 : Kp >= 96 ? 262144 : 786432;
+}
+bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias) {
+  static const int mode = [] {
+    const char* e = getenv("TGCN_EVAL_SCREEN");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  if (!eval_tc_screen_eligible(K, k, has_bias) || mode == 0) return false;
+  return mode == 1 || n_range >= screen_min_items(K);
+}
+
+int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k) {
+  if (!eval_tc_screen_eligible(K, k, false)) return -1;
+  const TcWorkspace w = tc_workspace(nullptr, n_rank, n_range, tc_padded_k(K, false), k, 1);
+  return (int64_t)((char*)w.ctrl - (char*)nullptr);
+}
+
+// Screen pass: approximate sweep + exact re-scoring + certificate; rows that fail are queued (gate_out describes the queue).
+int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users, int by_pos,
+                     const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
+                     int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
+                     int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, TcGate* gate_out,
+                     cudaStream_t s) {
+  const int Kp = tc_padded_k(K, false);
+  const int KC = Kp / TC_CHUNK;
+  const int64_t n_range = item_end - item_begin;
+  const int pm = pair_mode();
+  const bool pair = pm < 0 ? n_rank > TC_BM : pm == 1;
+  const int bn = 256;
+  const size_t a_bytes = (size_t)KC * TC_A_CHUNK_BYTES;
+  const size_t fixed = 1024 + a_bytes + kBarBlockBytes;
+  const size_t stage = (size_t)bn * 128 / (pair ? 2 : 1);
+  int n_stages = (int)((227 * 1024 - fixed) / stage);
+  if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
+  const size_t smem = fixed + (size_t)n_stages * stage;
+  const int kl = screen_kl(k);
+  TGCN_REQUIRE(n_stages >= 2 && (size_t)n_stages * stage >= (size_t)TC_BM * 3 * kl * 4 + TC_BM * 4, "item ring too small");
+  int n_splits, tps;
+  eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  const TcWorkspace w = tc_workspace(d_workspace, n_rank, n_range, Kp, k, n_splits);
+  TGCN_REQUIRE(d_workspace && workspace_bytes >= w.bytes, "workspace too small: need %lld bytes", (long long)w.bytes);
+  TGCN_CHECK_CUDA(cudaMemsetAsync(w.ctrl, 0, 256 + (size_t)n_rank * 4, s));
+  screen_prep_items_kernel<<<148 * 8, 256, 0, s>>>(d_item_vecs, ldi, item_begin, n_range, (int)K, w.i2, (unsigned*)(w.ctrl + 1));
+  TGCN_CHECK_LAUNCH();
+  const float* uptr = d_user_vecs;
+  int64_t uld = ldu;
+  if (!by_pos && d_users) {  // rows gathered by user id into list order
+    gather_rows_kernel<<<(unsigned)((n_rank * (K / 4) + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, d_users, n_rank, (int)K, w.u2);
+    TGCN_CHECK_LAUNCH();
+    uptr = w.u2;
+    uld = K;
+  }
+  CUtensorMap map_u, map_i;
+  if (int rc = make_map(&map_u, uptr, n_rank, K, TC_BM, uld)) return rc;
+  if (int rc = make_map(&map_i, w.i2, n_range, K, pair ? bn / 2 : bn, K)) return rc;
+  TcArgs a;
+  tc_args_common(&a, n_rank, Kp, K, n_range, item_begin, k, tps, n_stages, d_users, mrowptr, mcol, mrow_begin, mcol_off, w, n_splits, finalize,
+                 d_out_ids, d_out_scores);
+  a.ivec = d_item_vecs;
+  a.ldi = ldi;
+  a.eps_c = screen_eps_c();
+  a.max_inorm2 = (const unsigned*)(w.ctrl + 1);
+  a.fb_mark = w.fb_mark;
+  a.fb_rows = w.fb_rows;
+  a.fb_count = w.ctrl;
+  dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
+  if (pair) grid.x = (grid.x + 1) / 2 * 2;
+  int rc;
+  if (kl == 24) rc = pair ? tc_launch<256, 24, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 24, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
+  else if (kl == 32) rc = pair ? tc_launch<256, 32, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 32, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
+  else rc = pair ? tc_launch<256, 40, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
+  if (rc) return rc;
+  TGCN_CHECK_LAUNCH();
+  fb_index_kernel<<<(unsigned)((n_rank + 255) / 256), 256, 0, s>>>(w.fb_rows, w.ctrl, d_users, by_pos, (int)n_rank, w.fb_users, w.fb_src);
+  TGCN_CHECK_LAUNCH();
+  gate_out->count = w.ctrl;
+  gate_out->rows = w.fb_rows;
+  gate_out->users = w.fb_users;
+  gate_out->src = w.fb_src;
+  *n_splits_out = n_splits;
+  *part_ids_out = w.part_ids;
+  *part_scores_out = w.part_scores;
   return 0;
 }
 

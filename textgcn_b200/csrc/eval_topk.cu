@@ -258,6 +258,8 @@ struct MergeArgs {
   int finalize;
   int* out_ids;
   float* out_scores;
+  const int* n_rows_dev;  // device-gated second pass of the screened path: merge only the first *n_rows_dev rows ...
+  const int* out_rows;    // ... and write row r to out_rows[r]
 };
 
 // One warp per row: insert the n_parts·k candidates into a shared-memory list, then complete short
@@ -269,7 +271,8 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const MergeArgs a) {
   const int k = a.k;
   float* ls = reinterpret_cast<float*>(smem_raw) + wib * k;
   int* li = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + 4 * k) + wib * k;
-  if (row >= a.n_rows) return;
+  if (row >= a.n_rows || (a.n_rows_dev && row >= __ldg(a.n_rows_dev))) return;
+  const size_t orow = a.out_rows ? (size_t)__ldg(a.out_rows + row) : (size_t)row;
   for (int j = lane; j < k; j += 32) {
     ls[j] = -INFINITY;
     li[j] = INT_MAX;
@@ -304,8 +307,8 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const MergeArgs a) {
       id = t < deg ? __ldg(a.mcol + lo + t) - a.mcol_off : -1;
       s = -INFINITY;
     }
-    a.out_ids[(size_t)row * k + j] = id;
-    a.out_scores[(size_t)row * k + j] = s;
+    a.out_ids[orow * k + j] = id;
+    a.out_scores[orow * k + j] = s;
   }
 }
 
@@ -344,7 +347,15 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
                  int by_pos, const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
                  int64_t item_end, const float* d_user_bias, const float* d_item_bias, int32_t k, int finalize, int* d_out_ids,
                  float* d_out_scores, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
-                 float** part_scores_out, cudaStream_t s);
+                 float** part_scores_out, cudaStream_t s, const TcGate* gate);
+bool eval_tc_screen_eligible(int64_t K, int32_t k, bool has_bias);
+bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias);
+int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k);
+int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users, int by_pos,
+                     const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
+                     int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
+                     int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, TcGate* gate_out,
+                     cudaStream_t s);
 
 static int mask_fields(const tgcn_graph* g, const int** rowptr, const int** col, int* row_begin, int* col_off) {
   if (g) {
@@ -384,12 +395,14 @@ int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t
   return need;
 }
 
-int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_t* d_users, int32_t n_parts, int32_t k,
-                    const int32_t* d_part_ids, const float* d_part_scores, int32_t finalize, int32_t* d_out_ids,
-                    float* d_out_scores, tgcn_stream_t stream) {
+static int launch_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_t* d_users, int32_t n_parts, int32_t k,
+                        const int32_t* d_part_ids, const float* d_part_scores, int32_t finalize, int32_t* d_out_ids, float* d_out_scores,
+                        const int* n_rows_dev, const int* out_rows, tgcn_stream_t stream) {
   TGCN_REQUIRE(n_rows > 0 && n_parts > 0 && k > 0 && k <= TGCN_MAX_TOPK, "bad sizes: n_rows=%lld n_parts=%d k=%d", (long long)n_rows, n_parts, k);
   TGCN_REQUIRE(d_part_ids && d_part_scores && d_out_ids && d_out_scores, "NULL argument");
   MergeArgs m;
+  m.n_rows_dev = n_rows_dev;
+  m.out_rows = out_rows;
   m.users = d_users;
   m.n_rows = (int)n_rows;
   m.n_parts = n_parts;
@@ -406,6 +419,24 @@ int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_
   return 0;
 }
 
+int64_t tgcn_eval_screen_queue_offset(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k) {
+  if (n_rank <= 0 || n_items_range <= 0 || k <= 0 || K <= 0 || !eval_tc_eligible(K, k, false)) return -1;
+  return eval_tc_screen_queue_offset(n_rank, n_items_range, K, k);
+}
+
+int32_t tgcn_eval_resolve_precision(int64_t n_items_range, int64_t K, int32_t k, int32_t has_bias, int32_t precision) {
+  if (precision != 0) return precision;
+  if (!eval_tc_eligible(K, k, has_bias != 0)) return 1;
+  return eval_tc_screen_auto(n_items_range, K, k, has_bias != 0) ? 3 : 2;
+}
+
+int tgcn_topk_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const int32_t* d_users, int32_t n_parts, int32_t k,
+                    const int32_t* d_part_ids, const float* d_part_scores, int32_t finalize, int32_t* d_out_ids,
+                    float* d_out_scores, tgcn_stream_t stream) {
+  return launch_merge(mask_graph, n_rows, d_users, n_parts, k, d_part_ids, d_part_scores, finalize, d_out_ids, d_out_scores, nullptr, nullptr,
+                      stream);
+}
+
 int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users, const float* d_user_vecs,
                    int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin, int64_t item_end,
                    const float* d_user_bias, const float* d_item_bias, int32_t vecs_by_position, int32_t precision, int32_t k,
@@ -417,11 +448,11 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
   TGCN_REQUIRE(k > 0 && k <= TGCN_MAX_TOPK, "k=%d out of range (1..%d)", k, TGCN_MAX_TOPK);
   TGCN_REQUIRE(d_user_vecs && d_item_vecs && d_out_ids && d_out_scores, "NULL argument");
   TGCN_REQUIRE(((uintptr_t)d_user_vecs % 16 == 0) && ((uintptr_t)d_item_vecs % 16 == 0), "vector tables must be 16-byte aligned");
-  TGCN_REQUIRE(precision >= 0 && precision <= 2, "precision must be 0 (auto), 1 (fp32) or 2 (3xTF32)");
+  TGCN_REQUIRE(precision >= 0 && precision <= 3, "precision must be 0 (auto), 1 (fp32), 2 (3xTF32) or 3 (TF32 screen + exact re-scoring)");
   const int64_t need = tgcn_eval_workspace_bytes(n_rank, item_end - item_begin, K, k);
   TGCN_REQUIRE(d_workspace && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
   const bool tc_ok = eval_tc_eligible(K, k, d_user_bias || d_item_bias) && ldu % 4 == 0 && ldi % 4 == 0;
-  TGCN_REQUIRE(precision != 2 || tc_ok, "3xTF32 path needs k <= 64 (and K <= 8192)");
+  TGCN_REQUIRE((precision != 2 && precision != 3) || tc_ok, "the tensor-core paths need k <= 64 (and K <= 8192)");
   if (tc_ok && precision != 1) {
     const int* mrowptr;
     const int* mcol;
@@ -429,9 +460,30 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
     int* part_ids;
     float* part_scores;
     if (int rc = mask_fields(mask_graph, &mrowptr, &mcol, &mrow_begin, &mcol_off)) return rc;
+    const bool screen_ok = eval_tc_screen_eligible(K, k, d_user_bias || d_item_bias);
+    TGCN_REQUIRE(precision != 3 || screen_ok, "the screened path needs k <= 24, K <= 128 and no bias terms");
+    if (precision == 3 || (precision == 0 && eval_tc_screen_auto(item_end - item_begin, K, k, d_user_bias || d_item_bias))) {
+      // pass 1: one TF32 product per score, exact re-scoring of the candidates, certificate; pass 2 (gated on the device by the
+      // length of the queue pass 1 leaves): the 3xTF32 variant on the rows that could not be certified
+      TcGate gate;
+      if (int rc = eval_topk_screen(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi,
+                                    K, item_begin, item_end, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes, &n_splits,
+                                    &part_ids, &part_scores, &gate, (cudaStream_t)stream))
+        return rc;
+      if (n_splits > 1)
+        if (int rc = tgcn_topk_merge(mask_graph, n_rank, d_users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, stream))
+          return rc;
+      if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi, K,
+                                item_begin, item_end, nullptr, nullptr, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes,
+                                &n_splits, &part_ids, &part_scores, (cudaStream_t)stream, &gate))
+        return rc;
+      if (n_splits == 1) return 0;
+      return launch_merge(mask_graph, n_rank, gate.users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, gate.count,
+                          gate.rows, stream);
+    }
     if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs,
                               ldi, K, item_begin, item_end, d_user_bias, d_item_bias, k, finalize, d_out_ids, d_out_scores, d_workspace,
-                              workspace_bytes, &n_splits, &part_ids, &part_scores, (cudaStream_t)stream))
+                              workspace_bytes, &n_splits, &part_ids, &part_scores, (cudaStream_t)stream, nullptr))
       return rc;
     if (n_splits == 1) return 0;  // the kernel wrote (and completed) the final table itself
     return tgcn_topk_merge(mask_graph, n_rank, d_users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, stream);

@@ -161,7 +161,7 @@ class B200HotPath:
     """Mixin holding the kernel-backed overrides of BaseModel's hot-path methods."""
 
     dropout_rng = "host"  # "host": torch.rand on the CPU generator like base_model.py:82; "device": CUDA generator
-    eval_precision = "auto"  # "fp32" = exact FMA kernel; "3xtf32" = tcgen05 tensor cores; "auto" = 3xTF32 when eligible
+    eval_precision = "auto"  # "fp32" = exact FMA kernel; "3xtf32" / "screen" = tcgen05 tensor cores; "auto" = screen, else 3xTF32, else fp32
     strict_fused = False  # True: the methods that would materialise dense intermediates raise instead (score_batchwise, ...)
 
     # -- graph ---------------------------------------------------------------------------------

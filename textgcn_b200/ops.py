@@ -438,12 +438,17 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
               users: Optional[torch.Tensor] = None, n_rank: Optional[int] = None,
               item_range: Optional[Tuple[int, int]] = None, user_bias: Optional[torch.Tensor] = None,
               item_bias: Optional[torch.Tensor] = None, finalize: bool = True, by_position: bool = False,
-              precision: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
+              precision: str = "auto", stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused score + mask + top-k.  Returns (ids (n_rank, k) int32, scores (n_rank, k) fp32).
 
     ``users`` (int32 ids) selects the rows to rank and whose train items are masked; with ``by_position`` the
     user vectors / bias are already packed in list order (row m belongs to users[m]).
-    ``precision``: "fp32" (exact FMA, SIMT kernel), "3xtf32" (tcgen05 tensor cores) or "auto" (3xTF32 when eligible)."""
+    ``precision``: "fp32" (exact FMA, SIMT kernel), "3xtf32" (tcgen05 tensor cores, three TF32 products per score),
+    "screen" (one TF32 product per score to find the candidates, exact fp32 re-scoring of those, certificate per row, rows
+    that cannot be certified ranked again in 3xTF32; k <= 24, K <= 128, no bias) or "auto" (screen where the item range is long enough for it to pay — 131 072 rows at K = 128, 786 432 at
+    K = 64 —, else 3xTF32, else fp32).
+    ``stats`` (diagnostics; synchronises): a dict that receives ``precision`` (what the call ran at) and ``second_pass_rows``,
+    the number of rows a screened call had to rank again (None when the call did not take the screened path)."""
     lib = _lib.load()
     _chk(user_vecs, torch.float32, "user_vecs", 2)
     _chk(item_vecs, torch.float32, "item_vecs", 2)
@@ -459,7 +464,7 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
     dev = user_vecs.device
     ids = torch.empty((n_rank, k), dtype=torch.int32, device=dev)
     scores = torch.empty((n_rank, k), dtype=torch.float32, device=dev)
-    prec = {"auto": 0, "fp32": 1, "3xtf32": 2}[precision]
+    prec = _PRECISIONS[precision]
     nbytes = int(lib.tgcn_eval_workspace_bytes(n_rank, i1 - i0, K, k))
     if nbytes < 0:
         raise _lib.TgcnError("bad eval shape")
@@ -469,7 +474,21 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
                                  _ptr(user_vecs), user_vecs.stride(0), _ptr(item_vecs), item_vecs.stride(0), K, i0, i1,
                                  _ptr(user_bias), _ptr(item_bias), int(by_position), prec, k, int(finalize), _ptr(ids), _ptr(scores),
                                  _ptr(ws), ws.numel(), _stream()))
+    if stats is not None:
+        ran = int(lib.tgcn_eval_resolve_precision(i1 - i0, K, k, int(user_bias is not None or item_bias is not None), prec))
+        stats["precision"] = {1: "fp32", 2: "3xtf32", 3: "screen"}[ran]
+        off = int(lib.tgcn_eval_screen_queue_offset(n_rank, i1 - i0, K, k)) if ran == 3 else -1
+        stats["second_pass_rows"] = int(ws[off:off + 4].view(torch.int32).item()) if off >= 0 else None
     return ids, scores
+
+
+_PRECISIONS = {"auto": 0, "fp32": 1, "3xtf32": 2, "screen": 3}
+
+
+def eval_resolve_precision(n_items: int, K: int, k: int, has_bias: bool = False, precision: str = "auto") -> str:
+    """The precision an ``eval_topk`` call of this shape runs at ("fp32", "3xtf32" or "screen")."""
+    ran = int(_lib.load().tgcn_eval_resolve_precision(n_items, K, k, int(has_bias), _PRECISIONS[precision]))
+    return {1: "fp32", 2: "3xtf32", 3: "screen"}[ran]
 
 
 def topk_merge(mask_graph: Optional[Graph], part_ids: torch.Tensor, part_scores: torch.Tensor,

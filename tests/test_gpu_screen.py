@@ -76,6 +76,15 @@ def test_screen_near_duplicate_items_go_through_the_second_pass(ops, spread):
     if spread == 0.0:  # exact duplicates: canonical order (lowest ids of the plateau) — identical tables from every path
         ids32, _ = ops.eval_topk(None, ue, ie, k, precision="fp32")
         assert torch.equal(ids, ids32)
+    # item-sharded + merged (rows take the second pass in some shards and not in others): same exact scores, same table —
+    # except that items within the 3xTF32 error of each other (spread 1e-6) may swap at the k-th place
+    cuts = [0, 9000, 20000, ie.shape[0]]
+    parts = [ops.eval_topk(None, ue, ie, k, item_range=(a, b), finalize=False, precision="screen") for a, b in zip(cuts[:-1], cuts[1:])]
+    m_ids, m_sc = ops.topk_merge(None, torch.stack([p[0] for p in parts]).contiguous(), torch.stack([p[1] for p in parts]).contiguous())
+    if spread != 1e-6:
+        assert torch.equal(m_ids, ids) and torch.equal(m_sc, sc)
+    else:
+        _check(m_ids, m_sc, o_ids, o_sc, bound, max_inexact=n_rank)
 
 
 def test_screen_with_mask_gathered_users_ranges_and_merge(ops):

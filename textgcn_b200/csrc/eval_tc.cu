@@ -860,6 +860,53 @@ __global__ void __launch_bounds__(256) fb_index_kernel(const int* __restrict__ f
   fb_src[j] = (by_pos || !users) ? pos : user;
 }
 
+// Screened path, after the second pass: the rows it ranked carry 3xTF32 scores; give them the same exact fp32 scores (same FMA order as
+// screen_rescore) and order as every other row, so that a row's output does not depend on which pass produced it.  One warp per queue
+// entry, lane e = list position e (k <= 24).
+__global__ void __launch_bounds__(256) fb_rescore_kernel(const int* __restrict__ fb_rows, const int* __restrict__ fb_count, int n_rank,
+                                                         const int* __restrict__ users, int by_pos, const float* __restrict__ uvec, int64_t ldu,
+                                                         const float* __restrict__ ivec, int64_t ldi, int K, int k, int* __restrict__ out_ids,
+                                                         float* __restrict__ out_scores) {
+  const int lane = threadIdx.x & 31;
+  const int j = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (j >= min(n_rank, __ldg(fb_count))) return;
+  const int m = __ldg(fb_rows + j);
+  const int64_t src = (by_pos || !users) ? m : __ldg(users + m);
+  const size_t o = (size_t)m * k;
+  int id = INT_MAX;
+  float s = -INFINITY;
+  bool real = false;
+  if (lane < k) {
+    id = out_ids[o + lane];
+    s = out_scores[o + lane];
+    real = s != -INFINITY;  // short lists end with -inf entries (train items / sentinels): they keep their places
+    if (real) {
+      const float4* up = reinterpret_cast<const float4*>(uvec + src * ldu);
+      const float4* ip = reinterpret_cast<const float4*>(ivec + (size_t)id * ldi);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int g = 0; g < (K >> 2); ++g) {
+        const float4 x = __ldg(up + g), y = __ldg(ip + g);
+        acc[0] = fmaf(x.x, y.x, acc[0]);
+        acc[1] = fmaf(x.y, y.y, acc[1]);
+        acc[2] = fmaf(x.z, y.z, acc[2]);
+        acc[3] = fmaf(x.w, y.w, acc[3]);
+      }
+      s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+  }
+  int rank = 0;  // position among the real entries under (score desc, id asc)
+  for (int e = 0; e < k; ++e) {
+    const float se = __shfl_sync(0xffffffffu, s, e);
+    const int ie = __shfl_sync(0xffffffffu, id, e);
+    const bool re = __shfl_sync(0xffffffffu, real ? 1 : 0, e) != 0;
+    if (re && e != lane && ranks_before(se, ie, s, id)) ++rank;
+  }
+  if (lane < k && real) {
+    out_ids[o + rank] = id;
+    out_scores[o + rank] = s;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1176,6 +1223,14 @@ bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias) {
   }();
   if (!eval_tc_screen_eligible(K, k, has_bias) || mode == 0) return false;
   return mode == 1 || n_range >= screen_min_items(K);
+}
+
+int eval_tc_screen_rescore(const TcGate* gate, int64_t n_rank, const int32_t* d_users, int by_pos, const float* d_user_vecs, int64_t ldu,
+                           const float* d_item_vecs, int64_t ldi, int64_t K, int32_t k, int* d_out_ids, float* d_out_scores, cudaStream_t s) {
+  fb_rescore_kernel<<<(unsigned)((n_rank * 32 + 255) / 256), 256, 0, s>>>(gate->rows, gate->count, (int)n_rank, d_users, by_pos, d_user_vecs, ldu,
+                                                                        d_item_vecs, ldi, (int)K, k, d_out_ids, d_out_scores);
+  TGCN_CHECK_LAUNCH();
+  return 0;
 }
 
 int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k) {

@@ -351,6 +351,8 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
 bool eval_tc_screen_eligible(int64_t K, int32_t k, bool has_bias);
 bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias);
 int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k);
+int eval_tc_screen_rescore(const TcGate* gate, int64_t n_rank, const int32_t* d_users, int by_pos, const float* d_user_vecs, int64_t ldu,
+                           const float* d_item_vecs, int64_t ldi, int64_t K, int32_t k, int* d_out_ids, float* d_out_scores, cudaStream_t s);
 int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users, int by_pos,
                      const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
                      int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
@@ -477,9 +479,13 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
                                 item_begin, item_end, nullptr, nullptr, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes,
                                 &n_splits, &part_ids, &part_scores, (cudaStream_t)stream, &gate))
         return rc;
-      if (n_splits == 1) return 0;
-      return launch_merge(mask_graph, n_rank, gate.users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, gate.count,
-                          gate.rows, stream);
+      if (n_splits > 1)
+        if (int rc = launch_merge(mask_graph, n_rank, gate.users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores,
+                                  gate.count, gate.rows, stream))
+          return rc;
+      // the rows of the second pass get the same exact fp32 scores (and order) as the rest
+      return eval_tc_screen_rescore(&gate, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi, K, k, d_out_ids, d_out_scores,
+                                    (cudaStream_t)stream);
     }
     if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs,
                               ldi, K, item_begin, item_end, d_user_bias, d_item_bias, k, finalize, d_out_ids, d_out_scores, d_workspace,

@@ -210,8 +210,8 @@ int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch,
  * the TF32 error) is re-scored in exact fp32 FMA and the list re-sorted on the exact scores; this is provably the exact top-k unless
  * the band reaches the end of the 40 — such rows are queued on the device and ranked again by the 3xTF32 variant in the same call
  * (no host synchronisation: the second pass reads the queue length on the device); 0 = screened when eligible and the item range
- * is long enough for it to pay (131 072 rows at K = 128, 262 144 at K = 96, 786 432 at K <= 64: shorter sweeps are bound by the list
- * updates, which a 40-entry list doubles), else 3xTF32 when eligible, else fp32.  tgcn_eval_resolve_precision says what 0 resolves to for a shape.
+ * is long enough for it to pay (65 536 rows at K = 128, 98 304 at K = 96, 131 072 at K <= 64: shorter sweeps are dominated by the list
+ * updates of their opening, which the 40-entry list makes dearer), else 3xTF32 when eligible, else fp32.  tgcn_eval_resolve_precision says what 0 resolves to for a shape.
  * Outputs (n_rank, k) int32 ids and fp32 scores.  k <= TGCN_MAX_TOPK. */
 int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
 /* Byte offset, inside the eval workspace, of the int32 in which a screened call (precision 0 / 3) leaves the number of rows it

@@ -47,7 +47,7 @@ def test_screen_matches_fp64_on_ordinary_embeddings(ops, n_rank, n_items, d, k):
         stats = {}
         ids, sc = ops.eval_topk(None, ue, ie, k, precision=precision, stats=stats)
         _check(ids, sc, o_ids, o_sc, bound)
-        if precision == "screen" or (n_items >= 131072 and d > 96):  # auto: the screened path from 131 072 items on at K = 128
+        if precision == "screen" or n_items >= (65536 if d > 96 else 98304 if d > 64 else 131072):  # auto: long sweeps only
             assert stats["precision"] == "screen" and stats["second_pass_rows"] <= n_rank // 20, stats
         else:
             assert stats["precision"] == "3xtf32" and stats["second_pass_rows"] is None, stats

@@ -40,6 +40,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_CHUNK = 32;            // fp32 per 128-byte swizzle row
 constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
 constexpr int TC_MAX_STAGES = 8;
+constexpr int kInsRing = 16;           // INS variant: candidates a row can have in flight between its scanner threads and its inserter
+constexpr int kInsBytes = 2 * kInsRing * 128 * 4 + 3 * 128 * 4 + 64;  // rings (score, id) + tail / head / threshold per row + done counters
 constexpr int kBarBlockBytes = 256;   // mbarriers + the TMEM address slot ((10 + 2·TC_MAX_STAGES)·8 + 16 bytes, rounded up)
 
 struct TcArgs {
@@ -373,12 +375,19 @@ __device__ __noinline__ void screen_finalize(const ScreenFin f, int Kr, int k, c
 //                 waits for the slowest epilogue warp of the stage it is about to overwrite, has to wait for it — measured on the
 //                 screened pair variant and NOT adopted: c5 163.9 ms against 129.3 ms with two stages of 256 columns (the 128-column
 //                 MMA costs nearly as much per instruction as the 256-column one; profiles/r02/README.md).
-template <int BN, int KL, int EW, bool STREAM, int CTAS = 1, bool SCREEN = false, int NACC = 2>
-__global__ void __launch_bounds__(128 + 128 * EW, 1)
+// INS (screened variant): four more warps own the lists.  The epilogue ("scanner") threads only take the maximum of their scores and push
+//                 the few that beat the row's threshold into a small per-row ring in shared memory; inserter thread t keeps row t's ONE
+//                 sorted list in registers, pops the ring, applies the train-item mask and publishes the new threshold.  The list updates
+//                 — hundreds of instructions for one lane while its warp waits — leave the path that drains tensor memory, whose pace the
+//                 MMA issuer depends on (a stage is released by the slowest scanner warp), and the two column slices of a row share one
+//                 list and one threshold instead of keeping two.
+template <int BN, int KL, int EW, bool STREAM, int CTAS = 1, bool SCREEN = false, int NACC = 2, bool INS = false>
+__global__ void __launch_bounds__(128 + 128 * EW + (INS ? 128 : 0), 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
   static_assert(CTAS == 1 || (CTAS == 2 && !STREAM), "CTA pairs are implemented for the resident-user-tile variant");
   static_assert(!SCREEN || !STREAM, "screening is implemented for the resident-user-tile variant");
   static_assert(NACC * BN <= 512 && (NACC == 2 || NACC == 4), "tensor memory holds 512 accumulator columns");
+  static_assert(!INS || SCREEN, "inserter warps are implemented for the screened variant");
   constexpr bool PAIR = CTAS == 2;
   int n_rank = a.n_rank;
   if (a.n_rank_dev) n_rank = min(n_rank, __ldg(a.n_rank_dev));
@@ -403,6 +412,13 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   const uint32_t bar_t_empty = smem_u32(bars + 5 + 2 * TC_MAX_STAGES); // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * TC_MAX_STAGES);
 
+  float* rq_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBlockBytes);  // [kInsRing][128] (INS only)
+  int* rq_i = reinterpret_cast<int*>(rq_s + kInsRing * 128);                                   // [kInsRing][128], -1 = empty slot
+  int* rq_tail = rq_i + kInsRing * 128;                                                        // [128] pushes claimed
+  int* rq_head = rq_tail + 128;                                                                // [128] pops done
+  float* rq_thr = reinterpret_cast<float*>(rq_head + 128);                                     // [128] the row's current KL-th best
+  int* rq_done = reinterpret_cast<int*>(rq_thr + 128);                                         // [4] scanner warps of the quarter that finished
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
   const int n_tiles = (a.n_range + BN - 1) / BN;
@@ -424,6 +440,16 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       mbar_init(bar_t_empty + 8 * s, 4 * EW * CTAS);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (INS) {
+    if (warp >= 4 + 4 * EW) {
+      const int t = threadIdx.x - (128 + 128 * EW);
+      for (int e = 0; e < kInsRing; ++e) rq_i[e * 128 + t] = -1;
+      rq_tail[t] = 0;
+      rq_head[t] = 0;
+      rq_thr[t] = -INFINITY;
+      if (t < 4) rq_done[t] = 0;
+    }
   }
   if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers exist before anyone (TMA of the peer, remote arrives) touches them
   if (warp == 2) {
@@ -568,6 +594,170 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       }
     }
   } else if (warp >= 4) {
+    if constexpr (INS) {
+      constexpr int CW = BN / EW, NG = CW / 32;
+      static_assert(NG >= 2 && NG % 2 == 0, "the TMEM loads are double buffered two groups at a time");
+      const int q = warp & 3;  // TMEM lane quarter = row quarter
+      const int t = q * 32 + lane;
+      const int m = m0 + t;
+      const bool valid = m < n_rank;
+      float* ms = reinterpret_cast<float*>(ring) + (size_t)t * (3 * KL);  // the row's list after the sweep (item ring, idle by then)
+      int* mi = reinterpret_cast<int*>(ms + KL);
+      ScreenFin f;
+      f.ms = ms;
+      f.mi = mi;
+      f.me = ms + 2 * KL;
+      f.mp = reinterpret_cast<int*>(ring + (size_t)TC_BM * 3 * KL * 4) + t;
+      f.urow = gen_base + (size_t)t * 128;
+      f.t = t;
+      f.n_sub = EW + 1;
+      f.bar_id = 1 + q;
+      f.kl = KL;
+      f.m = m;
+      f.valid = valid;
+      f.mlo = 0;
+      f.mhi = 0;
+      f.split = blockIdx.y;
+      if (warp < 4 + 4 * EW) {
+        // ---- scanner: maximum of 32 scores against the row's published threshold; the rare hits go to the row's ring ----
+        const int sub = (warp - 4) >> 2;
+        volatile float* vthr = rq_thr + t;
+        volatile int* vhead = rq_head + t;
+        auto scan32 = [&](const uint32_t (&v)[32], int nbase) {
+          float mx[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+#pragma unroll
+          for (int j = 4; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(v[j]));
+          const float thr = *vthr;
+          if (!(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) > thr) || !valid) return;
+          uint32_t h4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (__uint_as_float(v[j]) > thr) h4[j & 3] |= 1u << j;
+          uint32_t hits = (h4[0] | h4[1]) | (h4[2] | h4[3]);
+          const int rem = a.n_range - nbase;  // columns past the item range hold zero-filled rows
+          if (rem < 32) hits &= rem > 0 ? (1u << rem) - 1u : 0u;
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const float s = pick32(v, j);
+            if (!(s > *vthr)) continue;  // the inserter may have raised the threshold meanwhile
+            const int slot = atomicAdd(rq_tail + t, 1);
+            if (slot - *vhead >= kInsRing) {  // ring full: wait for the inserter (bounded)
+              const long long t0 = clock64();
+              while (slot - *vhead >= kInsRing)
+                if (clock64() - t0 > 4000000000ll) __trap();
+            }
+            rq_s[(slot & (kInsRing - 1)) * 128 + t] = s;
+            __threadfence_block();
+            *reinterpret_cast<volatile int*>(rq_i + (slot & (kInsRing - 1)) * 128 + t) = a.item_begin + nbase + j;
+          }
+        };
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+          mbar_wait(bar_t_full + 8 * as, aphase);
+          tc_fence_after();
+          const int n0 = tile * BN + sub * CW;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + sub * CW;
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr, va);
+#pragma unroll 1
+          for (int g = 0; g < NG; g += 2) {
+            tmem_wait_ld();
+            tmem_ld32(taddr + (g + 1) * 32, vb);
+            scan32(va, n0 + g * 32);
+            tmem_wait_ld();
+            if (g + 2 < NG) tmem_ld32(taddr + (g + 2) * 32, va);
+            scan32(vb, n0 + (g + 1) * 32);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cta(bar_t_empty + 8 * as, 0);
+            else mbar_arrive(bar_t_empty + 8 * as);
+          }
+          if (++as == NACC) {
+            as = 0;
+            aphase ^= 1;
+          }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(rq_done + q, 1);  // every push of this warp is in shared memory
+        f.sub = 1 + sub;
+      } else {
+        // ---- inserter: row t's list (registers), Bloom filter and mask row; pops the row's ring until the quarter's scanners are done ----
+        const int user = valid ? (a.users ? __ldg(a.users + m) : m) : 0;
+        TGCN_DASSERT(!valid || !a.mrowptr || user >= a.mrow_begin);
+        int mlo = 0, mhi = 0;
+        if (valid && a.mrowptr) {
+          mlo = __ldg(a.mrowptr + user - a.mrow_begin);
+          mhi = __ldg(a.mrowptr + user - a.mrow_begin + 1);
+        }
+        uint32_t bloom[4] = {0u, 0u, 0u, 0u};
+        for (int p = mlo; p < mhi; ++p) {
+          const uint32_t b = (uint32_t)(__ldg(a.mcol + p) - a.mcol_off) & 127u;
+          bloom[0] |= (b >> 5) == 0 ? 1u << (b & 31) : 0u;
+          bloom[1] |= (b >> 5) == 1 ? 1u << (b & 31) : 0u;
+          bloom[2] |= (b >> 5) == 2 ? 1u << (b & 31) : 0u;
+          bloom[3] |= (b >> 5) == 3 ? 1u << (b & 31) : 0u;
+        }
+        float ls[KL];
+        int li[KL];
+#pragma unroll
+        for (int j = 0; j < KL; ++j) {
+          ls[j] = -INFINITY;
+          li[j] = INT_MAX;
+        }
+        float thr = -INFINITY;
+        int head = 0;
+        volatile int* vtail = rq_tail + t;
+        volatile int* vdone = rq_done + q;
+        long long t0 = clock64();  // of the last progress (the spins below are bounded: a protocol bug traps instead of hanging)
+        for (;;) {
+          const bool fin = *vdone == EW;  // read BEFORE the tail: a push precedes its warp's done count
+          const bool has = *vtail != head;
+          if (has) {
+            t0 = clock64();
+            volatile int* slot_i = rq_i + (head & (kInsRing - 1)) * 128 + t;
+            int item;
+            while ((item = *slot_i) < 0)  // claimed but not yet written
+              if (clock64() - t0 > 20000000000ll) __trap();
+            __threadfence_block();
+            const float s = *reinterpret_cast<volatile float*>(rq_s + (head & (kInsRing - 1)) * 128 + t);
+            *slot_i = -1;
+            __threadfence_block();
+            ++head;
+            *reinterpret_cast<volatile int*>(rq_head + t) = head;
+            if (s > thr) {
+              const uint32_t b = (uint32_t)item & 127u;
+              const uint32_t word = (b >> 5) == 0 ? bloom[0] : (b >> 5) == 1 ? bloom[1] : (b >> 5) == 2 ? bloom[2] : bloom[3];
+              if (!((word >> (b & 31)) & 1u) || !sorted_contains(a.mcol, mlo, mhi, item + a.mcol_off)) {
+                reg_list_insert<KL>(ls, li, s, item);  // (arrival is not in id order: the exact re-sort restores the canonical order)
+                thr = ls[KL - 1];
+                *reinterpret_cast<volatile float*>(rq_thr + t) = thr;
+              }
+            }
+          }
+          if (!__any_sync(0xffffffffu, has)) {
+            if (fin) break;
+            __nanosleep(64);
+            if (clock64() - t0 > 20000000000ll) __trap();
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < KL; ++j) {
+          ms[j] = ls[j];
+          mi[j] = li[j];
+        }
+        f.sub = 0;
+        f.mlo = mlo;
+        f.mhi = mhi;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * (EW + 1)) : "memory");  // the list is staged; scanners join the re-scoring
+      screen_finalize(f, a.Kr, a.k, a.ivec, a.ldi, a.eps_c, a.max_inorm2, a.fb_mark, a.fb_rows, a.fb_count, a.direct, a.finalize, a.mcol, a.mcol_off,
+                      a.n_rank, a.out_rows, a.out_ids, a.out_scores, a.part_ids, a.part_scores);
+    } else {
     // ---- epilogue: EW threads per user row, each scanning BN / EW columns of every tile ----
     constexpr int CW = BN / EW;       // columns per warp and tile
     constexpr int NG = CW / 32;       // 32-column groups per warp and tile
@@ -753,6 +943,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           a.part_ids[o + j] = li[j];
           a.part_scores[o + j] = ls[j];
         }
+    }
     }
     }
   }
@@ -1060,13 +1251,13 @@ int64_t eval_tc_workspace_bytes(int64_t n_rank, int64_t n_range, int64_t K, int3
 }
 
 
-template <int BN, int KL, int EW, bool ST, int CTAS, bool SCREEN, int NACC = 2>
+template <int BN, int KL, int EW, bool ST, int CTAS, bool SCREEN, int NACC = 2, bool INS = false>
 static int tc_launch(dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& map_u, const CUtensorMap& map_i, const TcArgs& a) {
-  auto kern = eval_topk_tc_kernel<BN, KL, EW, ST, CTAS, SCREEN, NACC>;
+  auto kern = eval_topk_tc_kernel<BN, KL, EW, ST, CTAS, SCREEN, NACC, INS>;
   TGCN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(128 + 128 * EW);
+  cfg.blockDim = dim3(128 + 128 * EW + (INS ? 128 : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1207,14 +1398,14 @@ bool eval_tc_screen_eligible(int64_t K, int32_t k, bool has_bias) {
   return !has_bias && K % 4 == 0 && K > 0 && tc_padded_k(K, false) <= 128 && k <= kScreenMaxK;
 }
 
-// precision 0 takes the screened path for long item sweeps only: on short ones the kernel is bound by the list updates of the sweep's
-// opening (every item beats an empty list), and a 40-entry list doubles those (c2, 63 k items: 15.0 ms screened, 8.6 ms 3xTF32; c5,
-// 2 M items: 126.6 ms against 271.7 ms).  The screened sweep costs about the same at every width (it is bound by its epilogue), the
-// 3xTF32 one grows with K, so the break-even moves: measured (75 776 users, random embeddings, tools/screen_crossover.py) at
-// ~110 k items for K = 128 and ~600 k for K = 64.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces it off / on where eligible.
+// precision 0 takes the screened path for long item sweeps only: a short sweep is dominated by its opening, where every item beats
+// an empty list, and the 40-entry list costs more there than the two TF32 products saved (c2, 63 k items, K = 64: 10.2 ms screened,
+// 8.6 ms 3xTF32; c5, 2 M items, K = 128: 107.7 ms against 267.2 ms).  The 3xTF32 sweep grows with K, the screened one much less, so the
+// break-even moves: measured (75 776 users, random embeddings, tools/screen_crossover.py) at ~50 k items for K = 128 and ~100 k for
+// K = 64.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces it off / on where eligible.
 static int64_t screen_min_items(int64_t K) {
   const int Kp = tc_padded_k(K, false);
-  return Kp >= 128 ? 131072 : Kp >= 96 ? 262144 : 786432;
+  return Kp >= 128 ? 65536 : Kp >= 96 ? 98304 : 131072;
 }
 bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias) {
   static const int mode = [] {
@@ -1251,8 +1442,13 @@ int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mc
   const int pm = pair_mode();
   const bool pair = pm < 0 ? n_rank > TC_BM : pm == 1;
   const int bn = 256;
+  static const bool ins_env = [] {  // TGCN_EVAL_SCREEN_INS = 0 (read once): A/B switch, lists back in the epilogue threads
+    const char* e = getenv("TGCN_EVAL_SCREEN_INS");
+    return !(e && atoi(e) == 0);
+  }();
+  const bool ins = ins_env && screen_kl(k) == 40;
   const size_t a_bytes = (size_t)KC * TC_A_CHUNK_BYTES;
-  const size_t fixed = 1024 + a_bytes + kBarBlockBytes;
+  const size_t fixed = 1024 + a_bytes + kBarBlockBytes + (ins ? kInsBytes : 0);
   const size_t stage = (size_t)bn * 128 / (pair ? 2 : 1);
   int n_stages = (int)((227 * 1024 - fixed) / stage);
   if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
@@ -1292,6 +1488,7 @@ int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mc
   int rc;
   if (kl == 24) rc = pair ? tc_launch<256, 24, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 24, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
   else if (kl == 32) rc = pair ? tc_launch<256, 32, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 32, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
+  else if (ins) rc = pair ? tc_launch<256, 40, 2, false, 2, true, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 1, true, 2, true>(grid, smem, s, map_u, map_i, a);
   else rc = pair ? tc_launch<256, 40, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
   if (rc) return rc;
   TGCN_CHECK_LAUNCH();

@@ -445,7 +445,7 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
     user vectors / bias are already packed in list order (row m belongs to users[m]).
     ``precision``: "fp32" (exact FMA, SIMT kernel), "3xtf32" (tcgen05 tensor cores, three TF32 products per score),
     "screen" (one TF32 product per score to find the candidates, exact fp32 re-scoring of those, certificate per row, rows
-    that cannot be certified ranked again in 3xTF32; k <= 24, K <= 128, no bias) or "auto" (screen where the item range is long enough for it to pay — 131 072 rows at K = 128, 786 432 at
+    that cannot be certified ranked again in 3xTF32; k <= 24, K <= 128, no bias) or "auto" (screen where the item range is long enough for it to pay — 65 536 rows at K = 128, 131 072 at
     K = 64 —, else 3xTF32, else fp32).
     ``stats`` (diagnostics; synchronises): a dict that receives ``precision`` (what the call ran at) and ``second_pass_rows``,
     the number of rows a screened call had to rank again (None when the call did not take the screened path)."""

@@ -315,9 +315,9 @@ def metrics_leg(ops, ids, n_users, n_items, k, dev, flush, torch, sample=20000):
 
 
 EVAL_PATHS = {
-    "screen": (1, "screen_prep_items_kernel + [gather_rows_kernel] + eval_topk_tc_kernel<SCREEN> (one TF32 tcgen05.mma per product on the raw "
-                  "tables, TMEM accumulators, TMA operands, CTA pairs; exact fp32 re-scoring + certificate in the kernel) + device-gated "
-                  "3xTF32 second pass for uncertified rows"),
+    "screen": (1, "screen_prep_items_kernel + [gather_rows_kernel] + eval_topk_tc_kernel<SCREEN, INS> (one TF32 tcgen05.mma per product on "
+                  "the raw tables, TMEM accumulators, TMA operands, CTA pairs, lists on inserter warps fed through shared-memory rings; "
+                  "exact fp32 re-scoring + certificate in the kernel) + device-gated 3xTF32 second pass for uncertified rows"),
     "3xtf32": (3, "tf32_split_kernel x2 + eval_topk_tc_kernel (3xTF32 tcgen05.mma, TMEM accumulators, TMA operands) + topk_merge_kernel"),
     "fp32": (0, "eval_topk_simt_kernel (exact fp32 FMA) + topk_merge_kernel"),
 }

@@ -384,7 +384,7 @@ __device__ __noinline__ void screen_finalize(const ScreenFin f, int Kr, int k, c
 template <int BN, int KL, int EW, bool STREAM, int CTAS = 1, bool SCREEN = false, int NACC = 2, bool INS = false>
 __global__ void __launch_bounds__(128 + 128 * EW + (INS ? 128 : 0), 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
-  static_assert(CTAS == 1 || (CTAS == 2 && !STREAM), "CTA pairs are implemented for the resident-user-tile variant");
+  static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair per 128 / 256 users");
   static_assert(!SCREEN || !STREAM, "screening is implemented for the resident-user-tile variant");
   static_assert(NACC * BN <= 512 && (NACC == 2 || NACC == 4), "tensor memory holds 512 accumulator columns");
   static_assert(!INS || SCREEN, "inserter warps are implemented for the screened variant");
@@ -400,7 +400,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   const int KC = a.K / TC_CHUNK;
   const int n_a = STREAM ? 0 : (SCREEN ? KC : 2 * KC);  // resident user chunks
   constexpr int BROWS = BN / CTAS;  // item rows of a tile held by THIS CTA's ring
-  constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BN * 128 : BROWS * 128;
+  constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BROWS * 128 : BROWS * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
   uint8_t* ring = gen_base + n_a * TC_A_CHUNK_BYTES;  // item ring; reused for the list merge once the sweep is over
@@ -473,16 +473,20 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       if constexpr (STREAM) {
+        auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+          if constexpr (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1);
+          else tma_load_2d(dst, map, bar, c0, c1);
+        };
         for (int tile = tile_begin; tile < tile_end; ++tile) {
-          const int row0 = tile * BN;
+          const int row0 = tile * BN + (int)cta_rank * BROWS;  // pair: this CTA streams its half of the item tile (and its own users)
           for (int kc = 0; kc < KC; ++kc) {
             const uint32_t st = sB + stage * B_STAGE_BYTES, full = bar_b_full + 8 * stage;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-            mbar_expect_tx(full, B_STAGE_BYTES);
-            tma_load_2d(st, &map_u, full, kc * TC_CHUNK, m0);
-            tma_load_2d(st + TC_A_CHUNK_BYTES, &map_u, full, a.K + kc * TC_CHUNK, m0);
-            tma_load_2d(st + 2 * TC_A_CHUNK_BYTES, &map_i, full, kc * TC_CHUNK, row0);
-            tma_load_2d(st + 2 * TC_A_CHUNK_BYTES + BN * 128, &map_i, full, a.K + kc * TC_CHUNK, row0);
+            if (leader) mbar_expect_tx(full, CTAS * B_STAGE_BYTES);
+            load(st, &map_u, full, kc * TC_CHUNK, m0);
+            load(st + TC_A_CHUNK_BYTES, &map_u, full, a.K + kc * TC_CHUNK, m0);
+            load(st + 2 * TC_A_CHUNK_BYTES, &map_i, full, kc * TC_CHUNK, row0);
+            load(st + 2 * TC_A_CHUNK_BYTES + BROWS * 128, &map_i, full, a.K + kc * TC_CHUNK, row0);
             if (++stage == a.n_stages) {
               stage = 0;
               phase ^= 1;
@@ -539,17 +543,17 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
             mbar_wait(bar_b_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t st = sB + stage * B_STAGE_BYTES;
-            const uint32_t a_hi = st, a_lo = st + TC_A_CHUNK_BYTES, b_hi = st + 2 * TC_A_CHUNK_BYTES, b_lo = b_hi + BN * 128;
+            const uint32_t a_hi = st, a_lo = st + TC_A_CHUNK_BYTES, b_hi = st + 2 * TC_A_CHUNK_BYTES, b_lo = b_hi + BROWS * 128;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_hi + kk * 32), idesc, accumulate);
+              mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_hi + kk * 32), accumulate);
               accumulate = 1;
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(b_hi + kk * 32), idesc, 1);
+            for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(b_hi + kk * 32), 1);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_lo + kk * 32), idesc, 1);
-            umma_commit(bar_b_empty + 8 * stage);
+            for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_lo + kk * 32), 1);
+            commit(bar_b_empty + 8 * stage);
             if (++stage == a.n_stages) {
               stage = 0;
               phase ^= 1;
@@ -1149,7 +1153,7 @@ static bool pair_wanted(int64_t n_range, int k) {
 
 static void tc_plan(int Kp, int* bn, int* n_stages, size_t* smem, bool* stream, bool want_pair = false, bool* pair = nullptr) {
   *stream = Kp > 128;
-  const bool use_pair = !*stream && want_pair;
+  const bool use_pair = want_pair;
   if (pair) *pair = use_pair;
   const size_t a_bytes = *stream ? 0 : (size_t)(2 * (Kp / TC_CHUNK)) * TC_A_CHUNK_BYTES;
   const size_t fixed = 1024 /*align slack*/ + a_bytes + kBarBlockBytes;
@@ -1307,10 +1311,14 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   int bn, n_stages;
   size_t smem;
   bool stream, pair;
-  tc_plan(Kp, &bn, &n_stages, &smem, &stream, pair_wanted(item_end - item_begin, k), &pair);
+  // CTA pairs: long sweeps of the resident variant (pair_wanted), and the streamed variant whenever there are two user tiles — it
+  // re-streams the whole item operand per user tile and is bound by L2 -> SM traffic, of which the pair halves the item share
+  const bool want_pair = Kp > 128 ? (k <= 40 && n_rank > TC_BM && pair_mode() != 0) : pair_wanted(item_end - item_begin, k);
+  tc_plan(Kp, &bn, &n_stages, &smem, &stream, want_pair, &pair);
   TGCN_REQUIRE(n_stages >= 2, "3xTF32 path does not fit in shared memory for K=%lld", (long long)K);
   {  // the list merge at the end of a sweep borrows the item ring: 128 rows x (score, id) x list capacity
-    const size_t stage_bytes = stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * (size_t)bn * 128 : (size_t)bn * 128 / (pair ? 2 : 1);
+    const size_t brows = (size_t)bn / (pair ? 2 : 1);
+    const size_t stage_bytes = stream ? (size_t)2 * TC_A_CHUNK_BYTES + 2 * brows * 128 : brows * 128;
     TGCN_REQUIRE((size_t)n_stages * stage_bytes >= (size_t)TC_BM * 2 * 40 * 4, "item ring too small for the list merge");
   }
   const int64_t n_range = item_end - item_begin;
@@ -1343,7 +1351,8 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
   if (pair) grid.x = (grid.x + 1) / 2 * 2;  // whole CTA pairs (a trailing CTA without users only lends its half of the item tile)
   int rc;
-  if (pair) rc = k <= 20 ? tc_launch<256, 20, 2, false, 2, false>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 2, false>(grid, smem, s, map_u, map_i, a);
+  if (pair && stream) rc = k <= 20 ? tc_launch<256, 20, 2, true, 2, false>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, true, 2, false>(grid, smem, s, map_u, map_i, a);
+  else if (pair) rc = k <= 20 ? tc_launch<256, 20, 2, false, 2, false>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 2, false>(grid, smem, s, map_u, map_i, a);
   else if (stream && bn == 256)
     rc = k <= 20   ? tc_launch<256, 20, 2, true, 1, false>(grid, smem, s, map_u, map_i, a)
          : k <= 40 ? tc_launch<256, 40, 2, true, 1, false>(grid, smem, s, map_u, map_i, a)

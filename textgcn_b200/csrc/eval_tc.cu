@@ -1,30 +1,40 @@
-// Full-ranking evaluation on the 5th-generation tensor cores: the user×item score GEMM runs as 3xTF32
-// tcgen05.mma (hi·hi + lo·hi + hi·lo, fp32 accumulation in TMEM) fused with train-item masking and a streaming
-// per-user top-k, so the score matrix exists only in tensor memory (base_model.py:255-261).
+// Full-ranking evaluation on the 5th-generation tensor cores: the user x item score GEMM runs on tcgen05.mma (fp32 accumulation
+// in TMEM) fused with train-item masking and a streaming per-user top-k, so the score matrix exists only in tensor memory
+// (base_model.py:255-261).  Two arithmetic schemes share one kernel template:
 //
-//   * Operands are pre-split once per call into [hi | lo] TF32 halves (hi = rna_tf32(x), lo = rna_tf32(x - hi);
-//     both have zero low mantissa bits, so the tensor core's input truncation is exact).  Dropping lo·lo bounds
-//     the relative product error by ~2^-21; scores agree with the fp32 SGEMM to ~1e-6 norm-wise (the parity
-//     budget is 1e-5), and are bit-exact whenever the inputs are TF32-representable (the tie fixture).
-//   * One CTA = 128 users × the whole item range (or one split of it).  The user tile (128 × 2K fp32) is loaded
-//     ONCE by TMA and stays resident in shared memory; item tiles of BN rows stream through an mbarrier ring of
-//     128-byte-swizzled K-chunks (32 fp32 = one swizzle row).  Warp 0 = TMA producer, warp 1 = MMA issuer
-//     (one elected thread), warp 2 = TMEM allocator, warps 4..4+4·EW-1 = epilogue (EW = 2: eight warps).  Item tiles are
-//     256 rows whenever three ring stages still fit: a 128×128×8 TF32 MMA measured ~117 cycles against 64 ideal.
-//   * Accumulators: 2 × BN TMEM columns (double buffered): the epilogue of tile t overlaps the MMAs of tile t+1.
-//   * Epilogue: TMEM lane = user row.  The EW warps of a lane quarter split every tile's COLUMNS, so a user row is
-//     scanned by EW threads, each with a private sorted list in REGISTERS over its share of the items; the lists are
-//     merged (lexicographic insert) once, after the sweep, through the then-idle item ring.  A thread reads 32
-//     scores with tcgen05.ld (the load of the next 32 in flight meanwhile), takes their MAXIMUM (one FMNMX per score,
-//     four independent chains) and compares it with its k-th best; only when that fires — ~k·(1 + ln(n/k)) times per
-//     sweep — does it build the 32-bit hit mask, consult a 128-bit register Bloom filter of the user's train items
-//     (exact binary search in the user row of Â only on a Bloom hit) and shift-insert.  Items arrive in increasing id
-//     order within a thread, so a strict '>' keeps the canonical (score desc, id asc) order.
-//     History (ncu, c2): row-split warps that each rebuilt a full hit mask for 32 rows but owned 16 ran the tensor
-//     pipe at 45 % — 0.37 warp instructions per score, 2 warps per scheduler with a tcgen05.wait::ld stall per group.
+//   * 3xTF32 (short item sweeps, k up to 64, bias terms, K > 128, and the second pass of the screened scheme): operands are pre-split
+//     once per call into [hi | lo] TF32 halves (hi = rna_tf32(x), lo = rna_tf32(x - hi); both have zero low mantissa bits, so the
+//     tensor core's input truncation is exact) and hi·hi + lo·hi + hi·lo is accumulated.  Dropping lo·lo bounds the relative product
+//     error by ~2^-21; scores agree with the fp32 SGEMM to ~1e-6 norm-wise (the parity budget is 1e-5) and are bit-exact whenever the
+//     inputs are TF32-representable (the tie fixture).
+//   * SCREEN (long item sweeps, k <= 24, K <= 128, no bias): ONE TF32 product per score from the raw user rows and a rounded copy of the
+//     item rows finds 40 candidates per user; those that can matter are re-scored in exact fp32 FMA and a per-row certificate decides
+//     whether the row is provably the exact top-k or must be ranked again by the 3xTF32 scheme (device-gated second pass).  See the
+//     SCREEN / INS template comments and screen_finalize below; DESIGN.md §4 has the derivation and the measurements.
 //
-// Roofline: tensor pipe, 3 × 2·K TF32 flops per score (MMA floor 128 cycles per 128×256×8 instruction).  Measured (ncu):
-// tensor pipe 93.6 % active at 2M items / d = 128 (871 TFLOP/s TF32), 49 % at 63k items / d = 64 (epilogue-bound).
+// Common structure:
+//   * One CTA = 128 users x the whole item range (or one split of it); CTA pairs (cta_group::2) share every 256-row item tile between
+//     two SMs on long sweeps.  The user tile is loaded ONCE by TMA and stays resident in shared memory (K <= 128; wider contractions
+//     stream it with the item tile); item tiles of BN rows stream through an mbarrier ring of 128-byte-swizzled K-chunks (32 fp32 = one
+//     swizzle row).  Warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator, warps 4..4+4·EW-1 =
+//     epilogue (EW = 2: eight warps), and for SCREEN four more "inserter" warps that own the lists.  Item tiles are 256 rows whenever
+//     three ring stages still fit: a 128x128x8 TF32 MMA measured ~117 cycles against 64 ideal.
+//   * Accumulators: 2 x BN TMEM columns (double buffered): the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * Epilogue: TMEM lane = user row.  The EW warps of a lane quarter split every tile's COLUMNS.  A thread reads 32 scores with
+//     tcgen05.ld (the load of the next 32 in flight meanwhile), takes their MAXIMUM (one FMNMX3 per two scores, four independent chains)
+//     and compares it with the row's k-th best; only when that fires — ~k·(1 + ln(n/k)) times per sweep — does it build the 32-bit hit
+//     mask and handle the candidates.  3xTF32: each of the row's EW threads keeps a private sorted list in REGISTERS over its share of
+//     the items, consults a 128-bit register Bloom filter of the user's train items (exact binary search in the user row of Â only on
+//     a Bloom hit) and shift-inserts; the lists are merged (lexicographic insert) once, after the sweep, through the then-idle item
+//     ring.  Items arrive in increasing id order within a thread, so a strict '>' keeps the canonical (score desc, id asc) order.
+//     SCREEN: the candidates go through a per-row ring in shared memory to the row's inserter thread (INS).
+//     History (ncu, c2): row-split warps that each rebuilt a full hit mask for 32 rows but owned 16 ran the tensor pipe at 45 % —
+//     0.37 warp instructions per score, 2 warps per scheduler with a tcgen05.wait::ld stall per group.
+//
+// Roofline: tensor pipe.  3xTF32: 3 x 2·K TF32 flops per score (MMA floor 128 cycles per 128x256x8 instruction); measured (ncu) tensor
+// pipe 93.6-95 % active at 2 M items / d = 128 (~860 TFLOP/s TF32 under the power cap), 49 % at 63 k items / d = 64 (bound by the list
+// updates of the sweep's opening).  SCREEN: 2·K flops per score; tensor pipe 78-85 % active at 2 M items / d = 128, 2.5 x the 3xTF32
+// scheme's users/s.
 #include <cuda.h>
 #include <limits.h>
 #include <math.h>

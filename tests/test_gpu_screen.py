@@ -137,3 +137,17 @@ def test_screen_few_rankable_items(ops):
     ids32, sc32 = ops.eval_topk(gr, ue, ie, k, precision="fp32")
     assert torch.equal(ids, ids32) and torch.equal(sc, sc32)
     assert bool((sc == -float("inf")).any())  # the fixture does contain short lists
+
+
+def test_screen_is_run_to_run_deterministic(ops):
+    """The candidates reach a row's inserter thread from two scanner threads in a timing-dependent order and uncertified rows are
+    queued with atomics; neither may show in the result."""
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    n_rank, n_items, d, k = 900, 150000, 128, 20
+    ue = torch.randn(n_rank, d, generator=gen, device=DEV) * 0.3
+    ie = (torch.randn(n_items // 50, d, generator=gen, device=DEV) * 0.3).repeat_interleave(50, dim=0)  # plateaus of exact ties
+    ie = ie * (1 + 1e-3 * torch.randn(ie.shape, generator=gen, device=DEV) * (torch.arange(n_items, device=DEV) % 3 == 0)[:, None])  # + near-ties inside the band
+    first = ops.eval_topk(None, ue, ie, k, precision="screen")
+    for _ in range(3):
+        again = ops.eval_topk(None, ue, ie, k, precision="screen")
+        assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1])

@@ -70,6 +70,7 @@ struct TcArgs {
   // device-gated re-run (the screened path's exact second pass): rank only the first *n_rank_dev rows, write row m to out_rows[m]
   const int* n_rank_dev;
   const int* out_rows;
+  int split_fastest;  // rasterisation: consecutive CTAs (pairs) take the SPLITS of one user tile (pair) instead of consecutive user tiles
   // screened variant: raw fp32 operands (1xTF32 scores), exact fp32 re-scoring of the candidates that matter, certificate
   int Kr;                         // real contraction width (K is padded to whole 32-wide chunks; TMA zero-fills the pad)
   const float* ivec;              // item table (row = item id) and its leading dimension, for the exact re-scoring
@@ -401,7 +402,17 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   constexpr bool PAIR = CTAS == 2;
   int n_rank = a.n_rank;
   if (a.n_rank_dev) n_rank = min(n_rank, __ldg(a.n_rank_dev));
-  if ((int)(blockIdx.x / CTAS * CTAS) * TC_BM >= n_rank) return;  // (a whole pair leaves together)
+  // Which user tile and which item split this CTA takes.  Default: blockIdx.x = user tile, blockIdx.y = split.  split_fastest: CTAs are
+  // scheduled in linear order (x fastest), and the streamed variant wants the CTAs that run at the same time to share user tiles —
+  // every CTA re-streams its 128 x 2K user tile once per item tile, and 148 different tiles of 1.7 MB (K = 1600) thrash the L2
+  // (ncu: 61.9 GB of DRAM reads per call, nearly all of it user operand) — so consecutive CTA groups take the splits of ONE tile group.
+  unsigned tile_x = blockIdx.x, split_y = blockIdx.y;
+  if (a.split_fastest) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x, grp = lin / CTAS;
+    split_y = grp % gridDim.y;
+    tile_x = (grp / gridDim.y) * CTAS + lin % CTAS;
+  }
+  if ((int)(tile_x / CTAS * CTAS) * TC_BM >= n_rank) return;  // (a whole pair leaves together)
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -430,9 +441,9 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   int* rq_done = reinterpret_cast<int*>(rq_thr + 128);                                         // [4] scanner warps of the quarter that finished
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM;
+  const int m0 = tile_x * TC_BM;
   const int n_tiles = (a.n_range + BN - 1) / BN;
-  const int tile_begin = blockIdx.y * a.tiles_per_split;
+  const int tile_begin = split_y * a.tiles_per_split;
   const int tile_end = min(n_tiles, tile_begin + a.tiles_per_split);
 
   if (warp == 0 && lane == 0) {
@@ -631,7 +642,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       f.valid = valid;
       f.mlo = 0;
       f.mhi = 0;
-      f.split = blockIdx.y;
+      f.split = split_y;
       if (warp < 4 + 4 * EW) {
         // ---- scanner: maximum of 32 scores against the row's published threshold; the rare hits go to the row's ring ----
         const int sub = (warp - 4) >> 2;
@@ -926,7 +937,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       f.valid = valid;
       f.mlo = mlo;
       f.mhi = mhi;
-      f.split = blockIdx.y;
+      f.split = split_y;
       screen_finalize(f, a.Kr, a.k, a.ivec, a.ldi, a.eps_c, a.max_inorm2, a.fb_mark, a.fb_rows, a.fb_count, a.direct, a.finalize, a.mcol, a.mcol_off,
                       a.n_rank, a.out_rows, a.out_ids, a.out_scores, a.part_ids, a.part_scores);
     } else {
@@ -950,7 +961,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
           a.out_scores[o + j] = s;
         }
     } else if (writer) {
-      const size_t o = ((size_t)blockIdx.y * a.n_rank + m) * a.k;
+      const size_t o = ((size_t)split_y * a.n_rank + m) * a.k;
 #pragma unroll
       for (int j = 0; j < KL; ++j)
         if (j < a.k) {
@@ -1226,6 +1237,35 @@ static void tc_fb_split_plan(int64_t n_rank, int64_t n_range, int bn, int* n_spl
   }
 }
 
+// Item splits of the STREAMED variant: every CTA re-streams its 128 x 2Kp user tile once per item tile, so the CTAs that run at the
+// same time should share user tiles (split_fastest rasterisation) and be few enough tiles that those stay in L2: enough splits that
+// 148 concurrent CTAs hold at most ~32 MB of user tiles, at least 16 item tiles per split.  TGCN_EVAL_STREAM_RASTER=0 (read once): off.
+static bool stream_raster_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("TGCN_EVAL_STREAM_RASTER");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+static void tc_stream_split_plan(int64_t n_rank, int64_t n_range, int64_t Kp, int bn, int* n_splits, int* tps) {
+  eval_split_plan(n_rank, n_range, bn, n_splits, tps);
+  if (!stream_raster_enabled()) return;
+  const int64_t n_tiles = (n_range + bn - 1) / bn;
+  const int64_t tile_bytes = (int64_t)TC_BM * 2 * Kp * 4;
+  static const int64_t target_mb = [] {  // experiment switch (read once): TGCN_EVAL_STREAM_L2_MB
+    const char* e = getenv("TGCN_EVAL_STREAM_L2_MB");
+    const int v = e ? atoi(e) : 0;
+    return (int64_t)(v > 0 ? v : 32);
+  }();
+  int64_t want = (148 * tile_bytes + (target_mb << 20) - 1) / (target_mb << 20);
+  if (want > n_tiles / 16) want = n_tiles / 16;
+  if (want > 16) want = 16;
+  if (want > *n_splits) {
+    *tps = (int)((n_tiles + want - 1) / want);
+    *n_splits = (int)((n_tiles + *tps - 1) / *tps);
+  }
+}
+
 struct TcWorkspace {
   float *u2, *i2;
   int* part_ids;
@@ -1239,7 +1279,12 @@ static TcWorkspace tc_workspace(void* base, int64_t n_rank, int64_t n_range, int
   int fs, fs2, ftps;
   tc_fb_split_plan(n_rank, n_range, 256, &fs, &ftps);
   tc_fb_split_plan(n_rank, n_range, 128, &fs2, &ftps);
-  const int64_t ns = std::max<int64_t>(n_splits, std::max(fs, fs2));
+  int64_t ns = std::max<int64_t>(n_splits, std::max(fs, fs2));
+  if (Kp > 128) {
+    int ss, stps;
+    tc_stream_split_plan(n_rank, n_range, Kp, 256, &ss, &stps);
+    ns = std::max<int64_t>(ns, ss);
+  }
   TcWorkspace w;
   char* p = (char*)base;
   auto take = [&](int64_t bytes) {
@@ -1334,6 +1379,7 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   const int64_t n_range = item_end - item_begin;
   int n_splits, tps;
   if (gate) tc_fb_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  else if (stream) tc_stream_split_plan(n_rank, n_range, Kp, bn, &n_splits, &tps);
   else eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
   const TcWorkspace w = tc_workspace(d_workspace, n_rank, n_range, Kp, k, n_splits);
   TGCN_REQUIRE(d_workspace && workspace_bytes >= w.bytes, "workspace too small: need %lld bytes", (long long)w.bytes);
@@ -1358,6 +1404,7 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
     a.n_rank_dev = gate->count;
     a.out_rows = gate->rows;
   }
+  a.split_fastest = (stream && n_splits > 1 && stream_raster_enabled()) ? 1 : 0;
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
   if (pair) grid.x = (grid.x + 1) / 2 * 2;  // whole CTA pairs (a trailing CTA without users only lends its half of the item tile)
   int rc;

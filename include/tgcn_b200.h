@@ -205,18 +205,20 @@ int tgcn_bpr_fwd_bwd(int64_t n_users, int64_t n_items, int64_t d, int64_t batch,
  * precision: 1 = exact fp32 FMA (SIMT kernel); 2 = 3xTF32 on the tcgen05 tensor cores (k <= 64; K is zero-padded to whole
  * 32-wide chunks, bias terms ride in one extra chunk; the user tile stays resident in shared memory for K <= 128 and is
  * streamed with the item tile above that; scores within ~1e-6 norm-wise of fp32, bit-exact for TF32-representable
- * inputs); 3 = screened (k <= 24, K <= 128, no bias terms): ONE TF32 product per score straight from the fp32 tables keeps the best
- * 40 items per user by approximate score, every kept item within 2·eps of the approximate k-th best (eps = 2.5e-3·|u|·max|i| bounds
- * the TF32 error) is re-scored in exact fp32 FMA and the list re-sorted on the exact scores; this is provably the exact top-k unless
- * the band reaches the end of the 40 — such rows are queued on the device and ranked again by the 3xTF32 variant in the same call
- * (no host synchronisation: the second pass reads the queue length on the device); 0 = screened when eligible and the item range
- * is long enough for it to pay (65 536 rows at K = 128, 98 304 at K = 96, 131 072 at K <= 64: shorter sweeps are dominated by the list
- * updates of their opening, which the 40-entry list makes dearer), else 3xTF32 when eligible, else fp32.  tgcn_eval_resolve_precision says what 0 resolves to for a shape.
+ * inputs); 3 = screened (k <= 24): ONE TF32 product per score (raw user rows x a rounded copy of the item rows; bias terms in an extra
+ * chunk) keeps the best 40 items per user by approximate score; with eps = 1.6e-3·|u|·max|i| (+ the bias terms' share) bounding the
+ * TF32 error, the k best of them are re-scored in exact fp32 FMA, further entries as long as approximate score + eps reaches the
+ * smallest of those exact scores, and the re-scored entries are sorted on the exact scores: provably the exact top-k unless no entry of
+ * a full list can be ruled out — such rows are queued on the device and ranked again by the 3xTF32 variant in the same call (no host
+ * synchronisation: the second pass reads the queue length on the device) and then given the same exact scores; 0 = screened when
+ * eligible without bias terms at K <= 128 and the item range is long enough for it to pay (65 536 rows at K = 128, 98 304 at K = 96,
+ * 131 072 at K <= 64: shorter sweeps are dominated by the list updates of their opening; wider contractions and bias terms have a
+ * screened form too, reachable with precision 3, which does not beat 3xTF32 yet), else 3xTF32 when eligible, else fp32.  tgcn_eval_resolve_precision says what 0 resolves to for a shape.
  * Outputs (n_rank, k) int32 ids and fp32 scores.  k <= TGCN_MAX_TOPK. */
 int64_t tgcn_eval_workspace_bytes(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
 /* Byte offset, inside the eval workspace, of the int32 in which a screened call (precision 0 / 3) leaves the number of rows it
  * sent to its second pass; -1 when the screened path does not apply to this shape.  Diagnostics only (bench, tests). */
-int64_t tgcn_eval_screen_queue_offset(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k);
+int64_t tgcn_eval_screen_queue_offset(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k, int32_t has_bias);
 /* The precision (1, 2 or 3) a tgcn_eval_topk call with this shape runs at: `precision` itself unless it is 0 (auto). */
 int32_t tgcn_eval_resolve_precision(int64_t n_items_range, int64_t K, int32_t k, int32_t has_bias, int32_t precision);
 int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t* d_users,

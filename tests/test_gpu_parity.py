@@ -212,7 +212,7 @@ def test_3xtf32_wide_and_ragged_contractions_with_bias(ops, n_rank, n_items, d, 
         full = ref + (ub[:, None].astype(np.float64) + ib[None, :] if bias else 0.0)
         o_ids, o_sc = O.canonical_topk(full, k)
         kw = dict(user_bias=_cuda(ub), item_bias=_cuda(ib)) if bias else {}
-        for precision in ("3xtf32", "fp32"):
+        for precision in ("3xtf32", "fp32") + (("screen",) if k <= 24 else ()):
             ids, sc = ops.eval_topk(None, _cuda(ue), _cuda(ie), k, precision=precision, **kw)
             assert np.array_equal(ids.cpu().numpy(), o_ids), (bias, precision)
             assert np.array_equal(sc.cpu().numpy(), o_sc.astype(np.float32)), (bias, precision)

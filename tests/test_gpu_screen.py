@@ -151,3 +151,35 @@ def test_screen_is_run_to_run_deterministic(ops):
     for _ in range(3):
         again = ops.eval_topk(None, ue, ie, k, precision="screen")
         assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1])
+
+
+@pytest.mark.parametrize("n_rank,n_items,d,k,bias", [(300, 20000, 1600, 20, True), (200, 30000, 260, 10, False), (257, 9000, 64, 20, True),
+                                                      (140, 70000, 128, 24, True)])
+def test_screen_streamed_form_with_bias_terms(ops, n_rank, n_items, d, k, bias):
+    """Wide contractions (the LTR score width) and bias terms take the streamed screened kernel: raw operands travel through the
+    ring chunk by chunk, the bias terms in one extra chunk whose share of the error bound is accounted separately, and the exact
+    re-scoring reads the user rows from global memory."""
+    gen = torch.Generator(device=DEV).manual_seed(d + n_items)
+    ue = torch.randn(n_rank, d, generator=gen, device=DEV) * (0.3 / (d / 64) ** 0.5)
+    ie = torch.randn(n_items, d, generator=gen, device=DEV) * (0.3 / (d / 64) ** 0.5)
+    ub = torch.randn(n_rank, generator=gen, device=DEV) * 0.5
+    ib = torch.randn(n_items, generator=gen, device=DEV) * 0.05
+    sc64 = ue.double() @ ie.double().T
+    if bias:
+        sc64 = sc64 + ub.double()[:, None] + ib.double()[None, :]
+    o_ids, o_sc = O.canonical_topk(sc64.cpu().numpy(), k)
+    bound = 1e-5 * float(ue.norm(dim=1).max() * ie.norm(dim=1).max() + (ub.abs().max() + ib.abs().max() if bias else 0))
+    kw = dict(user_bias=ub, item_bias=ib) if bias else {}
+    stats = {}
+    ids, sc = ops.eval_topk(None, ue, ie, k, precision="screen", stats=stats, **kw)
+    _check(ids, sc, o_ids, o_sc, bound)
+    assert stats["precision"] == "screen" and stats["second_pass_rows"] <= n_rank // 10, stats
+    # gathered users + mask-free item sub-ranges + merge give the same table
+    perm = torch.randperm(n_rank, generator=gen, device=DEV).to(torch.int32)
+    kw_g = dict(user_bias=ub, item_bias=ib) if bias else {}
+    ids_g, sc_g = ops.eval_topk(None, ue, ie, k, users=perm, precision="screen", **kw_g)
+    assert torch.equal(ids_g, ids[perm.long()]) and torch.equal(sc_g, sc[perm.long()])
+    cuts = [0, n_items // 4, n_items]
+    parts = [ops.eval_topk(None, ue, ie, k, item_range=(a, b), finalize=False, precision="screen", **kw) for a, b in zip(cuts[:-1], cuts[1:])]
+    m_ids, m_sc = ops.topk_merge(None, torch.stack([p[0] for p in parts]).contiguous(), torch.stack([p[1] for p in parts]).contiguous())
+    assert torch.equal(m_ids, ids) and torch.equal(m_sc, sc)

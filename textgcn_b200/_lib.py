@@ -56,7 +56,7 @@ SIGNATURES = {
     "tgcn_bpr_fwd_bwd": (c_int32, [c_int64, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float,
                                    _P, _P, _P, _P, c_int64, _P]),
     "tgcn_eval_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
-    "tgcn_eval_screen_queue_offset": (c_int64, [c_int64, c_int64, c_int64, c_int32]),
+    "tgcn_eval_screen_queue_offset": (c_int64, [c_int64, c_int64, c_int64, c_int32, c_int32]),
     "tgcn_eval_resolve_precision": (c_int32, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "tgcn_eval_topk": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P,
                                  c_int32, c_int32, c_int32, c_int32, _P, _P, _P, c_int64, _P]),

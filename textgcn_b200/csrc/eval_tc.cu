@@ -7,8 +7,8 @@
 //     tensor core's input truncation is exact) and hi·hi + lo·hi + hi·lo is accumulated.  Dropping lo·lo bounds the relative product
 //     error by ~2^-21; scores agree with the fp32 SGEMM to ~1e-6 norm-wise (the parity budget is 1e-5) and are bit-exact whenever the
 //     inputs are TF32-representable (the tie fixture).
-//   * SCREEN (long item sweeps, k <= 24, K <= 128, no bias): ONE TF32 product per score from the raw user rows and a rounded copy of the
-//     item rows finds 40 candidates per user; those that can matter are re-scored in exact fp32 FMA and a per-row certificate decides
+//   * SCREEN (long item sweeps, k <= 24; resident user tile for K <= 128 without bias terms, streamed otherwise): ONE TF32 product per
+//     score from the raw user rows and a rounded copy of the item rows finds 40 candidates per user; those that can matter are re-scored in exact fp32 FMA and a per-row certificate decides
 //     whether the row is provably the exact top-k or must be ranked again by the 3xTF32 scheme (device-gated second pass).  See the
 //     SCREEN / INS template comments and screen_finalize below; DESIGN.md §4 has the derivation and the measurements.
 //
@@ -70,6 +70,7 @@ struct TcArgs {
   // device-gated re-run (the screened path's exact second pass): rank only the first *n_rank_dev rows, write row m to out_rows[m]
   const int* n_rank_dev;
   const int* out_rows;
+  int chunk_major;    // streamed screened variant: operands stored K-chunk plane by plane ([KC][rows][32]); TMA row = kc·rows + r
   int split_fastest;  // rasterisation: consecutive CTAs (pairs) take the SPLITS of one user tile (pair) instead of consecutive user tiles
   // screened variant: raw fp32 operands (1xTF32 scores), exact fp32 re-scoring of the candidates that matter, certificate
   int Kr;                         // real contraction width (K is padded to whole 32-wide chunks; TMA zero-fills the pad)
@@ -77,6 +78,11 @@ struct TcArgs {
   int64_t ldi;
   float eps_c;                    // |s_tf32 - s| <= eps_c * |u| * |i|
   const unsigned* max_inorm2;     // bits of max_i |i|^2 over the ranked item range (written by screen_prep_items_kernel)
+  const float* ug;                // streamed screened variant: the raw user operand (n_rank, K) in the workspace — the exact rows for re-scoring
+  const float* ibias;             // item bias table (by item id) or NULL; the user bias sits in the operand's bias chunk
+  int has_bias;
+  float eps_ub, eps_ib;           // |error| <= ... + eps_ub·|ub| + eps_ib·max|ib| (bias chunk: [ub, 1] x [1, ib])
+  const unsigned* max_ib;         // bits of max |ib| over the ranked item range
   int* fb_mark;                   // per rank row: 1 once the row is queued for the exact second pass
   int* fb_rows;                   // queue of rank rows whose certificate failed
   int* fb_count;
@@ -255,15 +261,25 @@ struct ScreenFin {
   float* me;            // [kl] ... and room for their exact scores
   int* mp;              // one int per row
   const uint8_t* urow;  // the row in the resident user tile: chunk c at + c·16 KB, 16-byte unit q at ((q ^ (t & 7)) << 4)
+  const float* ug;      // streamed variant (no resident tile): the row's first chunk in the raw user operand (chunk-major: + ug_plane per chunk), else NULL
+  int64_t ug_plane;     // floats between two K-chunk planes of that operand
+  const float* ibias;   // item bias table (by item id) or NULL
+  float ub;             // user bias (0 without)
+  float eps_bias;       // what the bias terms add to the error bound
   int t, sub, n_sub, bar_id, kl, m, mlo, mhi, split;
   bool valid;
 };
 
+__device__ __forceinline__ float4 screen_user_unit(const ScreenFin& f, int g) {  // 16-byte unit g of the row's exact user vector
+  if (f.ug) return __ldg(reinterpret_cast<const float4*>(f.ug + (int64_t)(g >> 3) * f.ug_plane) + (g & 7));
+  return *reinterpret_cast<const float4*>(f.urow + (size_t)(g >> 3) * TC_A_CHUNK_BYTES + (((g & 7) ^ (f.t & 7)) << 4));
+}
+
 // exact fp32 score of list entries [lo, hi) — strided over the row's n_sub threads — from the fp32 tables
 __device__ __forceinline__ void screen_rescore(const ScreenFin& f, int lo, int hi, int k4, const float* __restrict__ ivec, int64_t ldi) {
-  const int t7 = f.t & 7;
   for (int j = lo + f.sub; j < hi; j += f.n_sub) {
-    const float4* ip = reinterpret_cast<const float4*>(ivec + (size_t)f.mi[j] * ldi);
+    const int id = f.mi[j];
+    const float4* ip = reinterpret_cast<const float4*>(ivec + (size_t)id * ldi);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int g0 = 0; g0 < k4; g0 += 8) {
       float4 iv[8];
@@ -271,14 +287,14 @@ __device__ __forceinline__ void screen_rescore(const ScreenFin& f, int lo, int h
       for (int q = 0; q < 8; ++q) iv[q] = g0 + q < k4 ? __ldg(ip + g0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 x = *reinterpret_cast<const float4*>(f.urow + (size_t)(g0 >> 3) * TC_A_CHUNK_BYTES + ((q ^ t7) << 4));
+        const float4 x = g0 + q < k4 ? screen_user_unit(f, g0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         acc[0] = fmaf(x.x, iv[q].x, acc[0]);
         acc[1] = fmaf(x.y, iv[q].y, acc[1]);
         acc[2] = fmaf(x.z, iv[q].z, acc[2]);
         acc[3] = fmaf(x.w, iv[q].w, acc[3]);
       }
     }
-    f.me[j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    f.me[j] = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + f.ub) + (f.ibias ? __ldg(f.ibias + id) : 0.f);
   }
 }
 
@@ -293,16 +309,16 @@ __device__ __noinline__ void screen_finalize(const ScreenFin f, int Kr, int k, c
                                              int finalize, const int* __restrict__ mcol, int mcol_off, int n_rank_stride,
                                              const int* __restrict__ out_rows, int* out_ids, float* out_scores, int* part_ids,
                                              float* part_scores) {
-  const int k4 = Kr >> 2, t7 = f.t & 7;
+  const int k4 = Kr >> 2;
   int n_valid = 0;
   float eps = 0.f;
   if (f.sub == 0) {
     float un2 = 0.f;
     for (int g = 0; g < k4; ++g) {
-      const float4 x = *reinterpret_cast<const float4*>(f.urow + (size_t)(g >> 3) * TC_A_CHUNK_BYTES + (((g & 7) ^ t7) << 4));
+      const float4 x = screen_user_unit(f, g);
       un2 = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, un2))));
     }
-    eps = eps_c * sqrtf(un2) * sqrtf(__uint_as_float(__ldg(max_inorm2)));
+    eps = eps_c * sqrtf(un2) * sqrtf(__uint_as_float(__ldg(max_inorm2))) + f.eps_bias;
     while (n_valid < f.kl && f.mi[n_valid] != INT_MAX) ++n_valid;
     *f.mp = n_valid < k ? n_valid : k;
   }
@@ -396,9 +412,10 @@ template <int BN, int KL, int EW, bool STREAM, int CTAS = 1, bool SCREEN = false
 __global__ void __launch_bounds__(128 + 128 * EW + (INS ? 128 : 0), 1)
 eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_i, const TcArgs a) {
   static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair per 128 / 256 users");
-  static_assert(!SCREEN || !STREAM, "screening is implemented for the resident-user-tile variant");
+  static_assert(!SCREEN || INS, "the screened variant runs with inserter warps");
   static_assert(NACC * BN <= 512 && (NACC == 2 || NACC == 4), "tensor memory holds 512 accumulator columns");
   static_assert(!INS || SCREEN, "inserter warps are implemented for the screened variant");
+  constexpr int PLANES = SCREEN ? 1 : 2;  // operand planes per K-chunk: the raw fp32 values, or their [hi | lo] TF32 halves
   constexpr bool PAIR = CTAS == 2;
   int n_rank = a.n_rank;
   if (a.n_rank_dev) n_rank = min(n_rank, __ldg(a.n_rank_dev));
@@ -421,7 +438,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
   const int KC = a.K / TC_CHUNK;
   const int n_a = STREAM ? 0 : (SCREEN ? KC : 2 * KC);  // resident user chunks
   constexpr int BROWS = BN / CTAS;  // item rows of a tile held by THIS CTA's ring
-  constexpr int B_STAGE_BYTES = STREAM ? 2 * TC_A_CHUNK_BYTES + 2 * BROWS * 128 : BROWS * 128;
+  constexpr int B_STAGE_BYTES = STREAM ? PLANES * (TC_A_CHUNK_BYTES + BROWS * 128) : BROWS * 128;
   const uint32_t sA = base;
   const uint32_t sB = sA + n_a * TC_A_CHUNK_BYTES;
   uint8_t* ring = gen_base + n_a * TC_A_CHUNK_BYTES;  // item ring; reused for the list merge once the sweep is over
@@ -504,10 +521,15 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
             const uint32_t st = sB + stage * B_STAGE_BYTES, full = bar_b_full + 8 * stage;
             mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
             if (leader) mbar_expect_tx(full, CTAS * B_STAGE_BYTES);
-            load(st, &map_u, full, kc * TC_CHUNK, m0);
-            load(st + TC_A_CHUNK_BYTES, &map_u, full, a.K + kc * TC_CHUNK, m0);
-            load(st + 2 * TC_A_CHUNK_BYTES, &map_i, full, kc * TC_CHUNK, row0);
-            load(st + 2 * TC_A_CHUNK_BYTES + BROWS * 128, &map_i, full, a.K + kc * TC_CHUNK, row0);
+            if constexpr (SCREEN) {  // one raw chunk of each operand (chunk-major layout: plane kc, contiguous boxes)
+              load(st, &map_u, full, 0, kc * a.n_rank + m0);
+              load(st + TC_A_CHUNK_BYTES, &map_i, full, 0, kc * a.n_range + row0);
+            } else {
+              load(st, &map_u, full, kc * TC_CHUNK, m0);
+              load(st + TC_A_CHUNK_BYTES, &map_u, full, a.K + kc * TC_CHUNK, m0);
+              load(st + 2 * TC_A_CHUNK_BYTES, &map_i, full, kc * TC_CHUNK, row0);
+              load(st + 2 * TC_A_CHUNK_BYTES + BROWS * 128, &map_i, full, a.K + kc * TC_CHUNK, row0);
+            }
             if (++stage == a.n_stages) {
               stage = 0;
               phase ^= 1;
@@ -564,16 +586,25 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
             mbar_wait(bar_b_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t st = sB + stage * B_STAGE_BYTES;
-            const uint32_t a_hi = st, a_lo = st + TC_A_CHUNK_BYTES, b_hi = st + 2 * TC_A_CHUNK_BYTES, b_lo = b_hi + BROWS * 128;
+            if constexpr (SCREEN) {
+              const uint32_t a_raw = st, b_raw = st + TC_A_CHUNK_BYTES;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_hi + kk * 32), accumulate);
-              accumulate = 1;
+              for (int kk = 0; kk < 4; ++kk) {
+                mma(d_tmem, umma_desc(a_raw + kk * 32), umma_desc(b_raw + kk * 32), accumulate);
+                accumulate = 1;
+              }
+            } else {
+              const uint32_t a_hi = st, a_lo = st + TC_A_CHUNK_BYTES, b_hi = st + 2 * TC_A_CHUNK_BYTES, b_lo = b_hi + BROWS * 128;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_hi + kk * 32), accumulate);
+                accumulate = 1;
+              }
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(b_hi + kk * 32), 1);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_lo + kk * 32), 1);
             }
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_lo + kk * 32), umma_desc(b_hi + kk * 32), 1);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) mma(d_tmem, umma_desc(a_hi + kk * 32), umma_desc(b_lo + kk * 32), 1);
             commit(bar_b_empty + 8 * stage);
             if (++stage == a.n_stages) {
               stage = 0;
@@ -634,6 +665,19 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
       f.me = ms + 2 * KL;
       f.mp = reinterpret_cast<int*>(ring + (size_t)TC_BM * 3 * KL * 4) + t;
       f.urow = gen_base + (size_t)t * 128;
+      f.ug = nullptr;
+      f.ug_plane = 0;
+      f.ibias = a.ibias;
+      f.ub = 0.f;
+      f.eps_bias = 0.f;
+      if constexpr (STREAM) {  // no resident tile: the exact user row comes from the raw operand in global memory (bias chunk last)
+        f.ug = a.ug + (size_t)(valid ? m : 0) * TC_CHUNK;
+        f.ug_plane = (int64_t)a.n_rank * TC_CHUNK;
+        if (a.has_bias) {
+          f.ub = __ldg(f.ug + (int64_t)(a.K / TC_CHUNK - 1) * f.ug_plane);
+          f.eps_bias = a.eps_ub * fabsf(f.ub) + a.eps_ib * __uint_as_float(__ldg(a.max_ib));
+        }
+      }
       f.t = t;
       f.n_sub = EW + 1;
       f.bar_id = 1 + q;
@@ -908,39 +952,7 @@ eval_topk_tc_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_cons
         asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EW) : "memory");
       }
     }
-    if constexpr (SCREEN) {
-      // ---- exact re-scoring of the band around the k-th best, certificate and output (see the template comment): a separate
-      // function with its own registers, so that none of it weighs on the sweep above; the lists travel through the idle ring
-      asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(128 * EW) : "memory");  // every quarter's merge is over: the ring is re-laid out
-      float* ms = reinterpret_cast<float*>(ring) + (size_t)t * (3 * KL);
-      int* mi = reinterpret_cast<int*>(ms + KL);
-      if (sub == 0) {
-#pragma unroll
-        for (int j = 0; j < KL; ++j) {
-          ms[j] = ls[j];
-          mi[j] = li[j];
-        }
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EW) : "memory");
-      ScreenFin f;
-      f.ms = ms;
-      f.mi = mi;
-      f.me = ms + 2 * KL;
-      f.mp = reinterpret_cast<int*>(ring + (size_t)TC_BM * 3 * KL * 4) + t;
-      f.urow = gen_base + (size_t)t * 128;
-      f.t = t;
-      f.sub = sub;
-      f.n_sub = EW;
-      f.bar_id = 1 + ew;
-      f.kl = KL;
-      f.m = m;
-      f.valid = valid;
-      f.mlo = mlo;
-      f.mhi = mhi;
-      f.split = split_y;
-      screen_finalize(f, a.Kr, a.k, a.ivec, a.ldi, a.eps_c, a.max_inorm2, a.fb_mark, a.fb_rows, a.fb_count, a.direct, a.finalize, a.mcol, a.mcol_off,
-                      a.n_rank, a.out_rows, a.out_ids, a.out_scores, a.part_ids, a.part_scores);
-    } else {
+    {
     const bool writer = valid && sub == 0;
     if (writer && a.direct) {
       int real = 0;  // the list is sorted, so sentinels (never-filled slots) come last
@@ -1026,31 +1038,69 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float* __restrict
   *reinterpret_cast<float4*>(out + r * 2 * Kp + Kp + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// Screened variant, item side: out (n_rows, K) = rna_tf32(src rows) — the tensor core then reads exactly these values, so the item
-// operand is off by at most 2^-11 relative instead of the 2^-10 of a 19-bit truncation — and the max |row|^2 of the exact rows.
+// Screened variant, item side: out (n_rows, Kp) = rna_tf32([src row | zero pad | bias chunk [1, ib, 0 ...] when bias terms exist]) — the
+// tensor core then reads exactly these values, so the item operand is off by at most 2^-11 relative instead of the 2^-10 of a 19-bit
+// truncation — plus the max |row|^2 of the exact rows and the max |ib|.
 __global__ void __launch_bounds__(256) screen_prep_items_kernel(const float* __restrict__ src, int64_t ld, int64_t row_begin, int64_t n_rows,
-                                                                int K, float* __restrict__ out, unsigned* __restrict__ max_norm2) {
+                                                                int K, int Kp, const float* __restrict__ ibias, int bias_chunk,
+                                                                int chunk_major, float* __restrict__ out, unsigned* __restrict__ max_norm2,
+                                                                unsigned* __restrict__ max_ib) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float best = 0.f;
+  float best = 0.f, best_b = 0.f;
   for (int64_t r = warp; r < n_rows; r += n_warps) {
     const float* row = src + (row_begin + r) * ld;
     float acc = 0.f;
-    for (int c = lane * 4; c < K; c += 128) {
-      const float4 x = ldg4(row + c);
-      acc = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, acc))));
+    for (int c = lane * 4; c < Kp; c += 128) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < K) {
+        x = ldg4(row + c);
+        acc = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, acc))));
+      } else if (bias_chunk && c == Kp - TC_CHUNK) {
+        const float b = ibias ? __ldg(ibias + row_begin + r) : 0.f;
+        x.x = 1.f;
+        x.y = b;
+        best_b = fmaxf(best_b, fabsf(b));
+      }
       uint32_t h[4];
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[0]) : "f"(x.x));
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[1]) : "f"(x.y));
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[2]) : "f"(x.z));
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[3]) : "f"(x.w));
-      *reinterpret_cast<uint4*>(out + r * K + c) = make_uint4(h[0], h[1], h[2], h[3]);
+      // chunk_major: plane kc holds the kc-th 32-wide K-chunk of every row, so that a TMA box of 128 rows is one contiguous 16 KB block
+      float* dst = chunk_major ? out + ((int64_t)(c >> 5) * n_rows + r) * TC_CHUNK + (c & 31) : out + r * Kp + c;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     best = fmaxf(best, acc);
   }
   if (lane == 0 && best > 0.f) atomicMax(max_norm2, __float_as_uint(best * 1.0001f));  // (any summation order stays below the bound)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best_b = fmaxf(best_b, __shfl_xor_sync(0xffffffffu, best_b, o));
+  if (lane == 0 && best_b > 0.f) atomicMax(max_ib, __float_as_uint(best_b));
+}
+
+// Streamed screened variant, user side: out (n_rows, Kp) = [src row (rows ? rows[r] : r) | zero pad | bias chunk [ub, 1, 0 ...]], raw fp32
+// (the exact rows the re-scoring reads; the tensor core truncates them itself).
+__global__ void __launch_bounds__(256) screen_prep_users_kernel(const float* __restrict__ src, int64_t ld, const int* __restrict__ rows,
+                                                                int64_t n_rows, int K, int Kp, const float* __restrict__ ubias,
+                                                                int bias_chunk, int chunk_major, float* __restrict__ out) {
+  const int k4 = Kp >> 2;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_rows * k4) return;
+  const int64_t r = t / k4;
+  const int c = (int)(t % k4) * 4;
+  const int64_t sr = rows ? (int64_t)__ldg(rows + r) : r;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < K) {
+    x = ldg4(src + sr * ld + c);
+  } else if (bias_chunk && c == Kp - TC_CHUNK) {
+    x.x = ubias ? __ldg(ubias + sr) : 0.f;
+    x.y = 1.f;
+  }
+  float* dst = chunk_major ? out + ((int64_t)(c >> 5) * n_rows + r) * TC_CHUNK + (c & 31) : out + r * Kp + c;
+  *reinterpret_cast<float4*>(dst) = x;
 }
 
 // out (n_rows, K) = src[rows[r], :K]
@@ -1081,8 +1131,9 @@ __global__ void __launch_bounds__(256) fb_index_kernel(const int* __restrict__ f
 // entry, lane e = list position e (k <= 24).
 __global__ void __launch_bounds__(256) fb_rescore_kernel(const int* __restrict__ fb_rows, const int* __restrict__ fb_count, int n_rank,
                                                          const int* __restrict__ users, int by_pos, const float* __restrict__ uvec, int64_t ldu,
-                                                         const float* __restrict__ ivec, int64_t ldi, int K, int k, int* __restrict__ out_ids,
-                                                         float* __restrict__ out_scores) {
+                                                         const float* __restrict__ ivec, int64_t ldi, int K, int k,
+                                                         const float* __restrict__ ubias, const float* __restrict__ ibias,
+                                                         int* __restrict__ out_ids, float* __restrict__ out_scores) {
   const int lane = threadIdx.x & 31;
   const int j = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   if (j >= min(n_rank, __ldg(fb_count))) return;
@@ -1107,7 +1158,7 @@ __global__ void __launch_bounds__(256) fb_rescore_kernel(const int* __restrict__
         acc[2] = fmaf(x.z, y.z, acc[2]);
         acc[3] = fmaf(x.w, y.w, acc[3]);
       }
-      s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      s = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + (ubias ? __ldg(ubias + src) : 0.f)) + (ibias ? __ldg(ibias + id) : 0.f);
     }
   }
   int rank = 0;  // position among the real entries under (score desc, id asc)
@@ -1247,11 +1298,11 @@ static bool stream_raster_enabled() {
   }();
   return on;
 }
-static void tc_stream_split_plan(int64_t n_rank, int64_t n_range, int64_t Kp, int bn, int* n_splits, int* tps) {
+static void tc_stream_split_plan(int64_t n_rank, int64_t n_range, int64_t Kp, int bn, int* n_splits, int* tps, int planes = 2) {
   eval_split_plan(n_rank, n_range, bn, n_splits, tps);
   if (!stream_raster_enabled()) return;
   const int64_t n_tiles = (n_range + bn - 1) / bn;
-  const int64_t tile_bytes = (int64_t)TC_BM * 2 * Kp * 4;
+  const int64_t tile_bytes = (int64_t)TC_BM * planes * Kp * 4;
   static const int64_t target_mb = [] {  // experiment switch (read once): TGCN_EVAL_STREAM_L2_MB
     const char* e = getenv("TGCN_EVAL_STREAM_L2_MB");
     const int v = e ? atoi(e) : 0;
@@ -1437,39 +1488,41 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
 // ---- screened variant -------------------------------------------------------------------------------------------------
 constexpr int kScreenKL = 40;       // list capacity of the screen
 constexpr int kScreenMaxK = 24;     // ... which leaves at least 16 entries of margin below the k-th best
-// experiment switch (read once): TGCN_EVAL_SCREEN_KL = 24 | 32 | 40
-static int screen_kl(int k) {
-  static const int v = [] {
-    const char* e = getenv("TGCN_EVAL_SCREEN_KL");
-    const int x = e ? atoi(e) : 0;
-    return (x == 24 || x == 32 || x == 40) ? x : kScreenKL;
-  }();
-  return v >= k + 4 ? v : kScreenKL;
-}
 // |s_tf32 - s| <= eps_c |u||i|: the user operand (raw fp32, so that the resident tile also serves the exact re-scoring) loses at most
 // 2^-10 of each element to the tensor core's 19-bit read, the item operand (rounded to nearest beforehand) 2^-11: 1.47e-3 on a product
-// with the cross term; the fp32 accumulation of K <= 128 exact products adds < 4e-5 (the 3xTF32 variant, same accumulation, agrees
-// with fp64 to ~1e-6); 1.6e-3 keeps 6 % in hand.  TGCN_EVAL_SCREEN_EPS overrides (experiments: a value too small makes the parity
-// tests fail, a large one sends every row to the second pass).
-static float screen_eps_c() {
+// with the cross term; the fp32 accumulation of the exact products adds < 4e-5 at K <= 128 (the 3xTF32 variant, same accumulation,
+// agrees with fp64 to ~1e-6); 1.6e-3 keeps 6 % in hand, and wide contractions (K = 1600) get 1.7e-3.  Bias terms ride in one extra
+// chunk as [ub, 1] x [1, ib]: ub·1 loses at most 2^-10 |ub| (1.1e-3 with slack), 1·ib at most 2^-11 |ib| (5.5e-4).
+// TGCN_EVAL_SCREEN_EPS overrides eps_c (experiments: a value too small makes the parity tests fail, a large one sends every row to the
+// second pass).
+static float screen_eps_c(int64_t K) {
   static const float c = [] {
     const char* e = getenv("TGCN_EVAL_SCREEN_EPS");
     const float v = e ? (float)atof(e) : 0.f;
-    return v > 0.f ? v : 1.6e-3f;
+    return v > 0.f ? v : 0.f;
   }();
-  return c;
+  return c > 0.f ? c : (K <= 128 ? 1.6e-3f : 1.7e-3f);
 }
 
 bool eval_tc_screen_eligible(int64_t K, int32_t k, bool has_bias) {
-  return !has_bias && K % 4 == 0 && K > 0 && tc_padded_k(K, false) <= 128 && k <= kScreenMaxK;
+  (void)has_bias;
+  return K % 4 == 0 && K > 0 && K <= 8192 && k <= kScreenMaxK;
 }
+
+// The streamed form (bias terms or K > 128) against the resident one
+static inline bool screen_streams(int64_t K, bool has_bias) { return has_bias || tc_padded_k(K, false) > 128; }
 
 // precision 0 takes the screened path for long item sweeps only: a short sweep is dominated by its opening, where every item beats
 // an empty list, and the 40-entry list costs more there than the two TF32 products saved (c2, 63 k items, K = 64: 10.2 ms screened,
 // 8.6 ms 3xTF32; c5, 2 M items, K = 128: 107.7 ms against 267.2 ms).  The 3xTF32 sweep grows with K, the screened one much less, so the
 // break-even moves: measured (75 776 users, random embeddings, tools/screen_crossover.py) at ~50 k items for K = 128 and ~100 k for
-// K = 64.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces it off / on where eligible.
-static int64_t screen_min_items(int64_t K) {
+// K = 64.  The STREAMED screened form (bias terms or K > 128: raw K-chunks of both operands travel through the ring, chunk-major
+// copies, exact re-scoring from global user rows) is built, tested and available as precision 3, but precision 0 does not take it: at
+// the LTR shape (K = 1600 + bias chunk, 63 k items, 18 944 users) it runs 17.3 ms against 14.1 ms for 3xTF32 — a third of the tensor
+// work, yet every 32 KB stage takes ~2000 cycles (ncu: tensor pipe 25 %, L2 hit 64 %, 27 GB of DRAM reads), the operand delivery and
+// not the MMAs set its pace.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces the screened path off / on where eligible.
+static int64_t screen_min_items(int64_t K, bool has_bias) {
+  if (screen_streams(K, has_bias)) return INT64_MAX;
   const int Kp = tc_padded_k(K, false);
   return Kp >= 128 ? 65536 : Kp >= 96 ? 98304 : 131072;
 }
@@ -1479,83 +1532,101 @@ bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias) {
     return e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
   if (!eval_tc_screen_eligible(K, k, has_bias) || mode == 0) return false;
-  return mode == 1 || n_range >= screen_min_items(K);
+  return mode == 1 || n_range >= screen_min_items(K, has_bias);
 }
 
 int eval_tc_screen_rescore(const TcGate* gate, int64_t n_rank, const int32_t* d_users, int by_pos, const float* d_user_vecs, int64_t ldu,
-                           const float* d_item_vecs, int64_t ldi, int64_t K, int32_t k, int* d_out_ids, float* d_out_scores, cudaStream_t s) {
+                           const float* d_item_vecs, int64_t ldi, int64_t K, int32_t k, const float* d_user_bias, const float* d_item_bias,
+                           int* d_out_ids, float* d_out_scores, cudaStream_t s) {
   fb_rescore_kernel<<<(unsigned)((n_rank * 32 + 255) / 256), 256, 0, s>>>(gate->rows, gate->count, (int)n_rank, d_users, by_pos, d_user_vecs, ldu,
-                                                                        d_item_vecs, ldi, (int)K, k, d_out_ids, d_out_scores);
+                                                                        d_item_vecs, ldi, (int)K, k, d_user_bias, d_item_bias, d_out_ids,
+                                                                        d_out_scores);
   TGCN_CHECK_LAUNCH();
   return 0;
 }
 
-int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k) {
-  if (!eval_tc_screen_eligible(K, k, false)) return -1;
-  const TcWorkspace w = tc_workspace(nullptr, n_rank, n_range, tc_padded_k(K, false), k, 1);
+int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, bool has_bias) {
+  if (!eval_tc_screen_eligible(K, k, has_bias)) return -1;
+  const TcWorkspace w = tc_workspace(nullptr, n_rank, n_range, tc_padded_k(K, has_bias), k, 1);
   return (int64_t)((char*)w.ctrl - (char*)nullptr);
 }
 
 // Screen pass: approximate sweep + exact re-scoring + certificate; rows that fail are queued (gate_out describes the queue).
 int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users, int by_pos,
                      const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
-                     int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
-                     int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, TcGate* gate_out,
-                     cudaStream_t s) {
-  const int Kp = tc_padded_k(K, false);
+                     int64_t item_end, const float* d_user_bias, const float* d_item_bias, int32_t k, int finalize, int* d_out_ids,
+                     float* d_out_scores, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
+                     float** part_scores_out, TcGate* gate_out, cudaStream_t s) {
+  const bool has_bias = d_user_bias != nullptr || d_item_bias != nullptr;
+  const bool stream = screen_streams(K, has_bias);
+  const int Kp = tc_padded_k(K, has_bias);  // (the bias chunk only exists in the streamed form)
   const int KC = Kp / TC_CHUNK;
   const int64_t n_range = item_end - item_begin;
   const int pm = pair_mode();
   const bool pair = pm < 0 ? n_rank > TC_BM : pm == 1;
   const int bn = 256;
-  static const bool ins_env = [] {  // TGCN_EVAL_SCREEN_INS = 0 (read once): A/B switch, lists back in the epilogue threads
-    const char* e = getenv("TGCN_EVAL_SCREEN_INS");
-    return !(e && atoi(e) == 0);
-  }();
-  const bool ins = ins_env && screen_kl(k) == 40;
-  const size_t a_bytes = (size_t)KC * TC_A_CHUNK_BYTES;
-  const size_t fixed = 1024 + a_bytes + kBarBlockBytes + (ins ? kInsBytes : 0);
-  const size_t stage = (size_t)bn * 128 / (pair ? 2 : 1);
+  const size_t brows = (size_t)bn / (pair ? 2 : 1);
+  const size_t a_bytes = stream ? 0 : (size_t)KC * TC_A_CHUNK_BYTES;
+  const size_t fixed = 1024 + a_bytes + kBarBlockBytes + kInsBytes;
+  const size_t stage = stream ? (size_t)TC_A_CHUNK_BYTES + brows * 128 : brows * 128;
   int n_stages = (int)((227 * 1024 - fixed) / stage);
   if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
   const size_t smem = fixed + (size_t)n_stages * stage;
-  const int kl = screen_kl(k);
-  TGCN_REQUIRE(n_stages >= 2 && (size_t)n_stages * stage >= (size_t)TC_BM * 3 * kl * 4 + TC_BM * 4, "item ring too small");
+  TGCN_REQUIRE(n_stages >= 2 && (size_t)n_stages * stage >= (size_t)TC_BM * 3 * kScreenKL * 4 + TC_BM * 4, "item ring too small");
   int n_splits, tps;
-  eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  if (stream) tc_stream_split_plan(n_rank, n_range, Kp, bn, &n_splits, &tps, 1);
+  else eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
   const TcWorkspace w = tc_workspace(d_workspace, n_rank, n_range, Kp, k, n_splits);
   TGCN_REQUIRE(d_workspace && workspace_bytes >= w.bytes, "workspace too small: need %lld bytes", (long long)w.bytes);
   TGCN_CHECK_CUDA(cudaMemsetAsync(w.ctrl, 0, 256 + (size_t)n_rank * 4, s));
-  screen_prep_items_kernel<<<148 * 8, 256, 0, s>>>(d_item_vecs, ldi, item_begin, n_range, (int)K, w.i2, (unsigned*)(w.ctrl + 1));
+  screen_prep_items_kernel<<<148 * 8, 256, 0, s>>>(d_item_vecs, ldi, item_begin, n_range, (int)K, Kp, d_item_bias, has_bias ? 1 : 0, stream ? 1 : 0,
+                                                  w.i2, (unsigned*)(w.ctrl + 1), (unsigned*)(w.ctrl + 2));
   TGCN_CHECK_LAUNCH();
   const float* uptr = d_user_vecs;
-  int64_t uld = ldu;
-  if (!by_pos && d_users) {  // rows gathered by user id into list order
+  int64_t uld = ldu, ucols = K;
+  if (stream) {  // the raw operand with zero pad and bias chunk, rows in list order
+    screen_prep_users_kernel<<<(unsigned)((n_rank * (Kp / 4) + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, (by_pos || !d_users) ? nullptr : d_users,
+                                                                                        n_rank, (int)K, Kp, d_user_bias, has_bias ? 1 : 0, 1, w.u2);
+    TGCN_CHECK_LAUNCH();
+    uptr = w.u2;
+    uld = ucols = Kp;
+  } else if (!by_pos && d_users) {  // rows gathered by user id into list order
     gather_rows_kernel<<<(unsigned)((n_rank * (K / 4) + 255) / 256), 256, 0, s>>>(d_user_vecs, ldu, d_users, n_rank, (int)K, w.u2);
     TGCN_CHECK_LAUNCH();
     uptr = w.u2;
     uld = K;
   }
   CUtensorMap map_u, map_i;
-  if (int rc = make_map(&map_u, uptr, n_rank, K, TC_BM, uld)) return rc;
-  if (int rc = make_map(&map_i, w.i2, n_range, K, pair ? bn / 2 : bn, K)) return rc;
+  if (stream) {  // chunk-major operands: 2-D maps over [KC · rows][32]
+    if (int rc = make_map(&map_u, w.u2, (int64_t)KC * n_rank, TC_CHUNK, TC_BM, TC_CHUNK)) return rc;
+    if (int rc = make_map(&map_i, w.i2, (int64_t)KC * n_range, TC_CHUNK, (int)brows, TC_CHUNK)) return rc;
+  } else {
+    if (int rc = make_map(&map_u, uptr, n_rank, ucols, TC_BM, uld)) return rc;
+    if (int rc = make_map(&map_i, w.i2, n_range, Kp, (int)brows, Kp)) return rc;
+  }
   TcArgs a;
   tc_args_common(&a, n_rank, Kp, K, n_range, item_begin, k, tps, n_stages, d_users, mrowptr, mcol, mrow_begin, mcol_off, w, n_splits, finalize,
                  d_out_ids, d_out_scores);
   a.ivec = d_item_vecs;
   a.ldi = ldi;
-  a.eps_c = screen_eps_c();
+  a.eps_c = screen_eps_c(K);
   a.max_inorm2 = (const unsigned*)(w.ctrl + 1);
+  a.ug = stream ? w.u2 : nullptr;
+  a.chunk_major = stream ? 1 : 0;
+  a.ibias = d_item_bias;
+  a.has_bias = has_bias ? 1 : 0;
+  a.eps_ub = 1.1e-3f;
+  a.eps_ib = 5.5e-4f;
+  a.max_ib = (const unsigned*)(w.ctrl + 2);
   a.fb_mark = w.fb_mark;
   a.fb_rows = w.fb_rows;
   a.fb_count = w.ctrl;
+  a.split_fastest = (stream && n_splits > 1 && stream_raster_enabled()) ? 1 : 0;
   dim3 grid((unsigned)((n_rank + TC_BM - 1) / TC_BM), (unsigned)n_splits);
   if (pair) grid.x = (grid.x + 1) / 2 * 2;
   int rc;
-  if (kl == 24) rc = pair ? tc_launch<256, 24, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 24, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
-  else if (kl == 32) rc = pair ? tc_launch<256, 32, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 32, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
-  else if (ins) rc = pair ? tc_launch<256, 40, 2, false, 2, true, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 1, true, 2, true>(grid, smem, s, map_u, map_i, a);
-  else rc = pair ? tc_launch<256, 40, 2, false, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, 40, 2, false, 1, true>(grid, smem, s, map_u, map_i, a);
+  if (stream) rc = pair ? tc_launch<256, kScreenKL, 2, true, 2, true, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, kScreenKL, 2, true, 1, true, 2, true>(grid, smem, s, map_u, map_i, a);
+  else rc = pair ? tc_launch<256, kScreenKL, 2, false, 2, true, 2, true>(grid, smem, s, map_u, map_i, a) : tc_launch<256, kScreenKL, 2, false, 1, true, 2, true>(grid, smem, s, map_u, map_i, a);
   if (rc) return rc;
   TGCN_CHECK_LAUNCH();
   fb_index_kernel<<<(unsigned)((n_rank + 255) / 256), 256, 0, s>>>(w.fb_rows, w.ctrl, d_users, by_pos, (int)n_rank, w.fb_users, w.fb_src);

@@ -350,14 +350,15 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
                  float** part_scores_out, cudaStream_t s, const TcGate* gate);
 bool eval_tc_screen_eligible(int64_t K, int32_t k, bool has_bias);
 bool eval_tc_screen_auto(int64_t n_range, int64_t K, int32_t k, bool has_bias);
-int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k);
+int64_t eval_tc_screen_queue_offset(int64_t n_rank, int64_t n_range, int64_t K, int32_t k, bool has_bias);
 int eval_tc_screen_rescore(const TcGate* gate, int64_t n_rank, const int32_t* d_users, int by_pos, const float* d_user_vecs, int64_t ldu,
-                           const float* d_item_vecs, int64_t ldi, int64_t K, int32_t k, int* d_out_ids, float* d_out_scores, cudaStream_t s);
+                           const float* d_item_vecs, int64_t ldi, int64_t K, int32_t k, const float* d_user_bias, const float* d_item_bias,
+                           int* d_out_ids, float* d_out_scores, cudaStream_t s);
 int eval_topk_screen(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_off, int64_t n_rank, const int32_t* d_users, int by_pos,
                      const float* d_user_vecs, int64_t ldu, const float* d_item_vecs, int64_t ldi, int64_t K, int64_t item_begin,
-                     int64_t item_end, int32_t k, int finalize, int* d_out_ids, float* d_out_scores, void* d_workspace,
-                     int64_t workspace_bytes, int* n_splits_out, int** part_ids_out, float** part_scores_out, TcGate* gate_out,
-                     cudaStream_t s);
+                     int64_t item_end, const float* d_user_bias, const float* d_item_bias, int32_t k, int finalize, int* d_out_ids,
+                     float* d_out_scores, void* d_workspace, int64_t workspace_bytes, int* n_splits_out, int** part_ids_out,
+                     float** part_scores_out, TcGate* gate_out, cudaStream_t s);
 
 static int mask_fields(const tgcn_graph* g, const int** rowptr, const int** col, int* row_begin, int* col_off) {
   if (g) {
@@ -421,9 +422,9 @@ static int launch_merge(const tgcn_graph_t* mask_graph, int64_t n_rows, const in
   return 0;
 }
 
-int64_t tgcn_eval_screen_queue_offset(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k) {
-  if (n_rank <= 0 || n_items_range <= 0 || k <= 0 || K <= 0 || !eval_tc_eligible(K, k, false)) return -1;
-  return eval_tc_screen_queue_offset(n_rank, n_items_range, K, k);
+int64_t tgcn_eval_screen_queue_offset(int64_t n_rank, int64_t n_items_range, int64_t K, int32_t k, int32_t has_bias) {
+  if (n_rank <= 0 || n_items_range <= 0 || k <= 0 || K <= 0 || !eval_tc_eligible(K, k, has_bias != 0)) return -1;
+  return eval_tc_screen_queue_offset(n_rank, n_items_range, K, k, has_bias != 0);
 }
 
 int32_t tgcn_eval_resolve_precision(int64_t n_items_range, int64_t K, int32_t k, int32_t has_bias, int32_t precision) {
@@ -463,29 +464,29 @@ int tgcn_eval_topk(const tgcn_graph_t* mask_graph, int64_t n_rank, const int32_t
     float* part_scores;
     if (int rc = mask_fields(mask_graph, &mrowptr, &mcol, &mrow_begin, &mcol_off)) return rc;
     const bool screen_ok = eval_tc_screen_eligible(K, k, d_user_bias || d_item_bias);
-    TGCN_REQUIRE(precision != 3 || screen_ok, "the screened path needs k <= 24, K <= 128 and no bias terms");
+    TGCN_REQUIRE(precision != 3 || screen_ok, "the screened path needs k <= 24");
     if (precision == 3 || (precision == 0 && eval_tc_screen_auto(item_end - item_begin, K, k, d_user_bias || d_item_bias))) {
       // pass 1: one TF32 product per score, exact re-scoring of the candidates, certificate; pass 2 (gated on the device by the
       // length of the queue pass 1 leaves): the 3xTF32 variant on the rows that could not be certified
       TcGate gate;
       if (int rc = eval_topk_screen(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi,
-                                    K, item_begin, item_end, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes, &n_splits,
-                                    &part_ids, &part_scores, &gate, (cudaStream_t)stream))
+                                    K, item_begin, item_end, d_user_bias, d_item_bias, k, finalize, d_out_ids, d_out_scores, d_workspace,
+                                    workspace_bytes, &n_splits, &part_ids, &part_scores, &gate, (cudaStream_t)stream))
         return rc;
       if (n_splits > 1)
         if (int rc = tgcn_topk_merge(mask_graph, n_rank, d_users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores, stream))
           return rc;
       if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi, K,
-                                item_begin, item_end, nullptr, nullptr, k, finalize, d_out_ids, d_out_scores, d_workspace, workspace_bytes,
-                                &n_splits, &part_ids, &part_scores, (cudaStream_t)stream, &gate))
+                                item_begin, item_end, d_user_bias, d_item_bias, k, finalize, d_out_ids, d_out_scores, d_workspace,
+                                workspace_bytes, &n_splits, &part_ids, &part_scores, (cudaStream_t)stream, &gate))
         return rc;
       if (n_splits > 1)
         if (int rc = launch_merge(mask_graph, n_rank, gate.users, n_splits, k, part_ids, part_scores, finalize, d_out_ids, d_out_scores,
                                   gate.count, gate.rows, stream))
           return rc;
       // the rows of the second pass get the same exact fp32 scores (and order) as the rest
-      return eval_tc_screen_rescore(&gate, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi, K, k, d_out_ids, d_out_scores,
-                                    (cudaStream_t)stream);
+      return eval_tc_screen_rescore(&gate, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs, ldi, K, k, d_user_bias, d_item_bias,
+                                    d_out_ids, d_out_scores, (cudaStream_t)stream);
     }
     if (int rc = eval_topk_tc(mrowptr, mcol, mrow_begin, mcol_off, n_rank, d_users, vecs_by_position, d_user_vecs, ldu, d_item_vecs,
                               ldi, K, item_begin, item_end, d_user_bias, d_item_bias, k, finalize, d_out_ids, d_out_scores, d_workspace,

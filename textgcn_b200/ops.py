@@ -445,7 +445,7 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
     user vectors / bias are already packed in list order (row m belongs to users[m]).
     ``precision``: "fp32" (exact FMA, SIMT kernel), "3xtf32" (tcgen05 tensor cores, three TF32 products per score),
     "screen" (one TF32 product per score to find the candidates, exact fp32 re-scoring of those, certificate per row, rows
-    that cannot be certified ranked again in 3xTF32; k <= 24, K <= 128, no bias) or "auto" (screen where the item range is long enough for it to pay — 65 536 rows at K = 128, 131 072 at
+    that cannot be certified ranked again in 3xTF32; k <= 24) or "auto" (screen where the item range is long enough for it to pay — 65 536 rows at K = 128, 131 072 at
     K = 64 —, else 3xTF32, else fp32).
     ``stats`` (diagnostics; synchronises): a dict that receives ``precision`` (what the call ran at) and ``second_pass_rows``,
     the number of rows a screened call had to rank again (None when the call did not take the screened path)."""
@@ -475,9 +475,10 @@ def eval_topk(mask_graph: Optional[Graph], user_vecs: torch.Tensor, item_vecs: t
                                  _ptr(user_bias), _ptr(item_bias), int(by_position), prec, k, int(finalize), _ptr(ids), _ptr(scores),
                                  _ptr(ws), ws.numel(), _stream()))
     if stats is not None:
-        ran = int(lib.tgcn_eval_resolve_precision(i1 - i0, K, k, int(user_bias is not None or item_bias is not None), prec))
+        biased = int(user_bias is not None or item_bias is not None)
+        ran = int(lib.tgcn_eval_resolve_precision(i1 - i0, K, k, biased, prec))
         stats["precision"] = {1: "fp32", 2: "3xtf32", 3: "screen"}[ran]
-        off = int(lib.tgcn_eval_screen_queue_offset(n_rank, i1 - i0, K, k)) if ran == 3 else -1
+        off = int(lib.tgcn_eval_screen_queue_offset(n_rank, i1 - i0, K, k, biased)) if ran == 3 else -1
         stats["second_pass_rows"] = int(ws[off:off + 4].view(torch.int32).item()) if off >= 0 else None
     return ids, scores
 

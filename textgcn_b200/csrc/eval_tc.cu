@@ -1277,11 +1277,17 @@ constexpr int kFbSplits = 8;
 void eval_split_plan(int64_t n_rank, int64_t n_items_range, int bn, int* n_splits, int* tiles_per_split);
 
 // Item splits of the device-gated second pass: it usually ranks a handful of rows, so a lone CTA would sweep the whole range.
-static void tc_fb_split_plan(int64_t n_rank, int64_t n_range, int bn, int* n_splits, int* tps) {
+static void tc_fb_split_plan(int64_t n_rank, int64_t n_range, int bn, int* n_splits, int* tps, int64_t Kp = 128, int32_t k = 20) {
   eval_split_plan(n_rank, n_range, bn, n_splits, tps);
   const int64_t n_tiles = (n_range + bn - 1) / bn;
-  int64_t want = n_tiles / 32;
-  if (want > kFbSplits) want = kFbSplits;
+  // about 128 K-chunk steps of 256 items per split (32 tiles at K = 128, 2-3 at the LTR width: one row queued there used to cost 2 ms),
+  // at most 32 splits, and partial tables of at most 256 MB (8 splits are always allowed)
+  const int64_t kc = (Kp + TC_CHUNK - 1) / TC_CHUNK;
+  int64_t want = n_tiles * kc / 128;
+  int64_t cap = (256ll << 20) / (n_rank * k * 8 > 0 ? n_rank * k * 8 : 1);
+  if (cap < kFbSplits) cap = kFbSplits;
+  if (cap > 32) cap = 32;
+  if (want > cap) want = cap;
   if (want > *n_splits) {
     *tps = (int)((n_tiles + want - 1) / want);
     *n_splits = (int)((n_tiles + *tps - 1) / *tps);
@@ -1303,11 +1309,14 @@ static void tc_stream_split_plan(int64_t n_rank, int64_t n_range, int64_t Kp, in
   if (!stream_raster_enabled()) return;
   const int64_t n_tiles = (n_range + bn - 1) / bn;
   const int64_t tile_bytes = (int64_t)TC_BM * planes * Kp * 4;
-  static const int64_t target_mb = [] {  // experiment switch (read once): TGCN_EVAL_STREAM_L2_MB
+  static const int64_t target_env = [] {  // experiment switch (read once): TGCN_EVAL_STREAM_L2_MB
     const char* e = getenv("TGCN_EVAL_STREAM_L2_MB");
     const int v = e ? atoi(e) : 0;
-    return (int64_t)(v > 0 ? v : 32);
+    return (int64_t)(v > 0 ? v : 0);
   }();
+  // measured at the LTR shape: 3xTF32 14.6 ms at 32 MB (8 splits), 15.0 at 64, 17.3 at 16; the screened form, whose every split pays
+  // the list updates of a sweep's opening again, 12.4 ms at 2 splits against 17.3 at 4 and 26.3 at 8
+  const int64_t target_mb = target_env > 0 ? target_env : (planes == 1 ? 64 : 32);
   int64_t want = (148 * tile_bytes + (target_mb << 20) - 1) / (target_mb << 20);
   if (want > n_tiles / 16) want = n_tiles / 16;
   if (want > 16) want = 16;
@@ -1328,8 +1337,8 @@ struct TcWorkspace {
 
 static TcWorkspace tc_workspace(void* base, int64_t n_rank, int64_t n_range, int64_t Kp, int32_t k, int n_splits) {
   int fs, fs2, ftps;
-  tc_fb_split_plan(n_rank, n_range, 256, &fs, &ftps);
-  tc_fb_split_plan(n_rank, n_range, 128, &fs2, &ftps);
+  tc_fb_split_plan(n_rank, n_range, 256, &fs, &ftps, Kp, k);
+  tc_fb_split_plan(n_rank, n_range, 128, &fs2, &ftps, Kp, k);
   int64_t ns = std::max<int64_t>(n_splits, std::max(fs, fs2));
   if (Kp > 128) {
     int ss, stps;
@@ -1429,7 +1438,7 @@ int eval_topk_tc(const int* mrowptr, const int* mcol, int mrow_begin, int mcol_o
   }
   const int64_t n_range = item_end - item_begin;
   int n_splits, tps;
-  if (gate) tc_fb_split_plan(n_rank, n_range, bn, &n_splits, &tps);
+  if (gate) tc_fb_split_plan(n_rank, n_range, bn, &n_splits, &tps, Kp, k);
   else if (stream) tc_stream_split_plan(n_rank, n_range, Kp, bn, &n_splits, &tps);
   else eval_split_plan(n_rank, n_range, bn, &n_splits, &tps);
   const TcWorkspace w = tc_workspace(d_workspace, n_rank, n_range, Kp, k, n_splits);
@@ -1518,9 +1527,10 @@ static inline bool screen_streams(int64_t K, bool has_bias) { return has_bias ||
 // break-even moves: measured (75 776 users, random embeddings, tools/screen_crossover.py) at ~50 k items for K = 128 and ~100 k for
 // K = 64.  The STREAMED screened form (bias terms or K > 128: raw K-chunks of both operands travel through the ring, chunk-major
 // copies, exact re-scoring from global user rows) is built, tested and available as precision 3, but precision 0 does not take it: at
-// the LTR shape (K = 1600 + bias chunk, 63 k items, 18 944 users) it runs 17.3 ms against 14.1 ms for 3xTF32 — a third of the tensor
-// work, yet every 32 KB stage takes ~2000 cycles (ncu: tensor pipe 25 %, L2 hit 64 %, 27 GB of DRAM reads), the operand delivery and
-// not the MMAs set its pace.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces the screened path off / on where eligible.
+// the LTR shape (K = 1600 + bias chunk, 63 k items, 18 944 users, random tables) it runs 11.1 ms against 14.4 ms for 3xTF32, a thin
+// margin that a full second pass would more than eat, and near-duplicate items (same text, slightly different graph embedding) sit
+// inside an error band that the wide text part of the operand makes large.  TGCN_EVAL_SCREEN = 0 / 1 (read once) forces the
+// screened path off / on where eligible.
 static int64_t screen_min_items(int64_t K, bool has_bias) {
   if (screen_streams(K, has_bias)) return INT64_MAX;
   const int Kp = tc_padded_k(K, false);

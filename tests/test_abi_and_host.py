@@ -50,6 +50,32 @@ def test_size_queries_and_argument_validation_without_gpu(lib):
     assert rc != 0 and handle.value is None
 
 
+def test_eval_precision_resolution_is_host_logic(lib, monkeypatch):
+    """Which of the three eval paths a call takes is decided on the host from the shape alone (include/tgcn_b200.h, precision):
+    the screened path for long item sweeps of narrow, bias-free contractions; 3xTF32 otherwise; fp32 where the tensor-core
+    kernels do not apply.  An explicit precision is returned unchanged."""
+    for var in ("TGCN_EVAL_SCREEN",):
+        monkeypatch.delenv(var, raising=False)
+    res = lambda n_items, K, k, bias=0, prec=0: lib.tgcn_eval_resolve_precision(n_items, K, k, bias, prec)  # noqa: E731
+    assert res(2_000_000, 128, 20) == 3          # c5: screened
+    assert res(63_000, 64, 20) == 2              # c2: short sweep stays on 3xTF32
+    assert res(65_536, 128, 20) == 3 and res(65_535, 128, 20) == 2
+    assert res(131_072, 64, 20) == 3 and res(131_071, 64, 20) == 2
+    assert res(98_304, 96, 20) == 3 and res(98_303, 96, 20) == 2
+    assert res(2_000_000, 128, 25) == 2          # k > 24: no margin in the 40-entry list
+    assert res(2_000_000, 128, 20, bias=1) == 2  # bias terms / wide contractions: the streamed screened form is opt-in
+    assert res(63_000, 1600, 20, bias=1) == 2
+    assert res(63_000, 1600, 65) == 1            # k > 64: exact fp32 kernel
+    assert res(63_000, 62, 20) == 1              # K % 4 != 0
+    for prec in (1, 2, 3):
+        assert res(63_000, 64, 20, prec=prec) == prec
+    # the diagnostics offset exists exactly where the screened path can run, and lies inside the workspace
+    for n_rank, n_items, K, k, bias in ((2048, 2_000_000, 128, 20, 0), (300, 20_000, 1600, 20, 1), (64, 500, 32, 1, 0)):
+        off = lib.tgcn_eval_screen_queue_offset(n_rank, n_items, K, k, bias)
+        assert 0 <= off < lib.tgcn_eval_workspace_bytes(n_rank, n_items, K, k) - 4
+    assert lib.tgcn_eval_screen_queue_offset(2048, 2_000_000, 128, 30, 0) == -1
+
+
 def test_product_refuses_cpu_tensors_and_never_imports_the_oracle():
     from textgcn_b200 import TgcnError, ops
     with pytest.raises(TgcnError):

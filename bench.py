@@ -415,7 +415,7 @@ def c2_leg(args, dev, flush, torch, hbm_peak):
         h_i = torch.empty((ni, d), dtype=torch.float32).pin_memory().copy_(w["iw"].cpu())
         h_o = torch.empty((n, d), dtype=torch.float32).pin_memory()
         stage = torch.empty((2 * n, d), dtype=torch.float32, device=dev)
-        te = timed_steps(lambda: ops.propagate_host(graph, h_u, h_i, h_o, L, stage), 5, 2, flush, torch)
+        te = timed_steps(lambda: ops.propagate_host(graph, h_u, h_i, h_o, L, stage), 5, 3, flush, torch)
         torch.cuda.synchronize()
         res["e2e"] = {"value": nnz * L / (sum(te) / len(te) * 1e-3), "unit": "edges/s", "ms_per_step": sum(te) / len(te),
                       "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4,
@@ -426,7 +426,7 @@ def c2_leg(args, dev, flush, torch, hbm_peak):
         st = {}
         ops.eval_topk(graph, out[:nu], out[nu:], k, users=users, stats=st)
         mma = EVAL_PATHS[st["precision"]][0]
-        te = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], k, users=users), args.eval_steps, 1, flush, torch)
+        te = timed_steps(lambda: ops.eval_topk(graph, out[:nu], out[nu:], k, users=users), args.eval_steps, 3, flush, torch)
         ems = sum(te) / len(te)
         res["eval"] = {"users_per_s": nu / (ems * 1e-3), "ms": ems, "k": k, "n_users_ranked": nu, "precision": st["precision"],
                        "second_pass_rows": st["second_pass_rows"], "kernel": EVAL_PATHS[st["precision"]][1],
@@ -883,7 +883,7 @@ def main():
                 h_oi.copy_(out_i, non_blocking=True)
         if world > 1:
             dist.barrier()
-        et = timed_steps(e2e_step, max(3, args.steps // 2), 2, flush, torch)
+        et = timed_steps(e2e_step, max(3, args.steps // 2), 3, flush, torch)
         e_ms = torch.tensor([sum(et) / len(et)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
@@ -959,7 +959,7 @@ def main():
                 a_ids, a_sc = eval_step()
                 b_ids, b_sc = eval_item_sharded()
                 extra.update(sharded_eval_agreement(a_ids, a_sc, b_ids, b_sc, torch))
-                t_is = timed_steps(eval_item_sharded, args.eval_steps, 1, flush, torch)
+                t_is = timed_steps(eval_item_sharded, args.eval_steps, 3, flush, torch)
                 is_ms = torch.tensor([sum(t_is) / len(t_is)], dtype=torch.float64, device=dev)
                 dist.all_reduce(is_ms, op=dist.ReduceOp.MAX)
                 extra["eval_item_sharded"] = {"users_per_s": n_eval / (float(is_ms) * 1e-3), "ms": float(is_ms),
@@ -987,13 +987,13 @@ def main():
                 a_ids, a_sc = eval_step()
                 b_ids, b_sc = eval_item_sharded()
                 extra.update(sharded_eval_agreement(a_ids, a_sc, b_ids, b_sc, torch))
-                t_is = timed_steps(eval_item_sharded, args.eval_steps, 1, flush, torch)
+                t_is = timed_steps(eval_item_sharded, args.eval_steps, 3, flush, torch)
                 is_ms = torch.tensor([sum(t_is) / len(t_is)], dtype=torch.float64, device=dev)
                 dist.all_reduce(is_ms, op=dist.ReduceOp.MAX)
                 extra["eval_item_sharded"] = {"users_per_s": n_eval / (float(is_ms) * 1e-3), "ms": float(is_ms),
                                               "sharding": f"item range x{world}, all-to-all of partial top-k + merge"}
             eval_e2e = None
-        t_ev = timed_steps(eval_step, args.eval_steps, 1, flush, torch)
+        t_ev = timed_steps(eval_step, args.eval_steps, 3, flush, torch)
         ev_ms = torch.tensor([sum(t_ev) / len(t_ev)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ev_ms, op=dist.ReduceOp.MAX)
@@ -1024,7 +1024,7 @@ def main():
         if world == 1 and name == "c5":
             ev["metrics_10M_users"] = metrics_leg(ops, eval_step()[0], nu, ni, k, dev, flush, torch)
         if eval_e2e is not None:
-            t_e = timed_steps(eval_e2e, args.eval_steps, 1, flush, torch)
+            t_e = timed_steps(eval_e2e, args.eval_steps, 3, flush, torch)
             ev["e2e_users_per_s"] = n_eval / (sum(t_e) / len(t_e) * 1e-3)
             ev["e2e_h2d_bytes"] = n_eval * 4
             ev["e2e_d2h_bytes"] = n_eval * k * 8

@@ -85,3 +85,29 @@ def test_wide_band_flags_instead_of_guessing():
     assert flagged
     ids, flagged = screen_rule(approx, lambda i: float(exact[i]), eps=1e-4, k=20, kl=40)
     assert not flagged and ids == list(range(20))
+
+
+# ---- the split-fastest rasterisation of the streamed eval variant (eval_tc.cu, `split_fastest`) ---------------------------------
+def _raster(bx, by, gx, gy, ctas):
+    """(blockIdx.x, blockIdx.y) -> (user tile, item split), restating the kernel's index arithmetic."""
+    lin = by * gx + bx
+    grp = lin // ctas
+    return (grp // gy) * ctas + lin % ctas, grp % gy
+
+
+@pytest.mark.parametrize("gx,gy,ctas", [(148, 8, 2), (6, 3, 2), (7, 4, 1), (2, 1, 2), (1, 5, 1), (150, 2, 2)])
+def test_split_fastest_rasterisation_is_a_bijection_that_keeps_pairs_together(gx, gy, ctas):
+    seen = {}
+    for by in range(gy):
+        for bx in range(gx):
+            seen[(bx, by)] = _raster(bx, by, gx, gy, ctas)
+    assert sorted(seen.values()) == [(t, s) for t in range(gx) for s in range(gy)]  # every (tile, split) exactly once
+    if ctas == 2:  # the two CTAs of a cluster (adjacent blockIdx.x, same blockIdx.y) take adjacent user tiles of the SAME split
+        for by in range(gy):
+            for bx in range(0, gx, 2):
+                (t0, s0), (t1, s1) = seen[(bx, by)], seen[(bx + 1, by)]
+                assert s0 == s1 and t1 == t0 + 1 and t0 % 2 == 0
+    # CTAs are scheduled in linear order: consecutive groups walk the splits of one tile group before moving to the next
+    order = [seen[(lin % gx, lin // gx)] for lin in range(gx * gy)]
+    tiles_in_order = [t // ctas for t, _ in order]
+    assert tiles_in_order == sorted(tiles_in_order)
